@@ -1,0 +1,460 @@
+// kmc_api.cu -- C ABI of libkmcb200.so (see include/kmc_b200.h).
+//
+// Part 1: the cgo exports of the reference's libSimulation.so, re-implemented on the B200 hop
+//         kernels (goSimulation/simulationWrapper.go:83-169, 274-316).
+// Part 2: lean ensemble API.
+// There is NO CPU fallback: without a CUDA device every entry point fails loudly.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/kmc_b200.h"
+#include "kmc_internal.cuh"
+
+using namespace kmcb200;
+
+// ---------------------------------------------------------------- errors / globals
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+static std::atomic<uint64_t> g_seed{0x6b6d635f646e5f31ULL};  // "kmc_dn_1"
+static std::atomic<uint64_t> g_next_member{0};
+
+static int fail(const std::string &msg) {
+    g_err = msg;
+    return 1;
+}
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e__);                      \
+            return 1;                                                                         \
+        }                                                                                     \
+    } while (0)
+
+struct kmcb200_layout {
+    int device = 0;
+    LayoutDev dev{};
+    // grow-only device workspace for host-pointer calls
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    std::mutex mu;
+};
+
+extern "C" int kmcb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" const char *kmcb200_last_error(void) { return g_err.c_str(); }
+extern "C" const char *kmcb200_version(void) { return "kmcb200 0.1 (sm_100a)"; }
+extern "C" int kmcb200_sizeof_ensemble_args(void) { return (int)sizeof(kmcb200_ensemble_args); }
+extern "C" void kmcb200_set_seed(uint64_t seed) {
+    g_seed.store(seed);
+    g_next_member.store(0);
+}
+extern "C" long long kmcb200_launch_count(void) { return g_launches.load(); }
+
+// ---------------------------------------------------------------- layout
+template <typename T>
+static int upload(T **dst, const std::vector<T> &src) {
+    CU(cudaMalloc((void **)dst, sizeof(T) * (src.empty() ? 1 : src.size())));
+    if (!src.empty()) CU(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const double *distances,
+                                                 const double *transitions_constant, double nu, double I_0,
+                                                 double R, double prune_threshold) {
+    if (N < 0 || P < 0 || N + P <= 0 || !distances || !transitions_constant) {
+        fail("kmcb200_layout_create: bad arguments");
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fail("kmcb200: no CUDA device available (this library has no CPU fallback)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        fail("kmcb200_layout_create: device index out of range");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail("kmcb200_layout_create: cudaSetDevice failed");
+        return nullptr;
+    }
+    const int S = N + P;
+    auto *lay = new kmcb200_layout();
+    lay->device = device;
+    LayoutDev &D = lay->dev;
+    D.N = N; D.P = P; D.S = S;
+    D.slots = (S + 31) / 32;
+    D.pitch2 = 32 * D.slots + 1;
+    D.nu32 = (float)nu; D.I032 = (float)I_0; D.R32 = (float)R;  // simulationWrapper.go:92
+    D.nu64 = nu; D.I064 = I_0; D.R64 = R;
+
+    std::vector<float> d32((size_t)S * S), tc32((size_t)S * S);
+    std::vector<double> d64(distances, distances + (size_t)S * S), tc64(transitions_constant, transitions_constant + (size_t)S * S);
+    for (size_t k = 0; k < (size_t)S * S; ++k) { d32[k] = (float)distances[k]; tc32[k] = (float)transitions_constant[k]; }
+    // simulation.go:199-215: transition list = pairs with tc > cut*max(tc), row-major
+    float largest = 0.0f;
+    for (float v : tc32) if (largest < v) largest = v;
+    const float cut = (float)prune_threshold;
+    std::vector<int2> pairs;
+    std::vector<uint8_t> keep((size_t)S * S, 0);
+    for (int i = 0; i < S; ++i)
+        for (int j = 0; j < S; ++j)
+            if (tc32[(size_t)i * S + j] > cut * largest) { pairs.push_back(make_int2(i, j)); keep[(size_t)i * S + j] = 1; }
+    D.L = (int)pairs.size();
+    // fast table [target j][source i]
+    std::vector<float2> tbl((size_t)S * D.pitch2, make_float2(0.f, 0.f));
+    const float IR = D.I032 * D.R32;
+    for (int j = 0; j < S; ++j)
+        for (int i = 0; i < S; ++i) {
+            float2 v = make_float2(0.f, 0.f);
+            const bool ee = (i >= N && j >= N);
+            if (i != j && !ee && keep[(size_t)i * S + j]) v.x = D.nu32 * tc32[(size_t)i * S + j];
+            if (i != j && i < N && j < N) v.y = IR / d32[(size_t)i * S + j];
+            tbl[(size_t)j * D.pitch2 + i] = v;
+        }
+    int rc = upload(&D.tbl, tbl) || upload(&D.d32, d32) || upload(&D.tc32, tc32) || upload(&D.d64, d64) ||
+             upload(&D.tc64, tc64) || upload(&D.pairs, pairs);
+    if (rc) {
+        delete lay;
+        return nullptr;
+    }
+    return lay;
+}
+
+extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
+    if (!lay) return;
+    cudaSetDevice(lay->device);
+    cudaFree(lay->dev.tbl); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
+    cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
+    cudaFree(lay->ws);
+    delete lay;
+}
+
+// ---------------------------------------------------------------- ensemble run
+namespace {
+struct Carver {  // bump allocator over the layout workspace, 256-byte aligned
+    char *base; size_t off = 0;
+    template <typename T> T *take(size_t n) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off += (n * sizeof(T) + 255) & ~size_t(255);
+        return p;
+    }
+};
+size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
+}  // namespace
+
+static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
+    if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");
+    if (a->B < 0 || a->hops < 0 || a->prehops < 0) return fail("kmcb200_run_ensemble: negative size");
+    if (a->mode < 0 || a->mode > 3) return fail("kmcb200_run_ensemble: unknown mode");
+    if (!a->E_constant && !(a->basis && a->electrode_v)) return fail("kmcb200_run_ensemble: need E_constant or basis+electrode_v");
+    if (lay->dev.P > 0 && !a->electrode_v) return fail("kmcb200_run_ensemble: electrode_v is required");
+    if (!a->kT || !a->time || !a->electrode_occ) return fail("kmcb200_run_ensemble: kT/time/electrode_occ are required");
+    if (a->mode == KMCB200_MODE_PY && !a->stream_u64) return fail("kmcb200_run_ensemble: MODE_PY replays an injected stream (stream_u64)");
+    if ((a->mode == KMCB200_MODE_GO_SIMULATE || a->mode == KMCB200_MODE_GO_RECORDPLUS) && !(a->stream_e && a->stream_u))
+        return fail("kmcb200_run_ensemble: Go replay modes need stream_e and stream_u");
+    if (a->mode == KMCB200_MODE_FAST && ((a->stream_e != nullptr) != (a->stream_u != nullptr)))
+        return fail("kmcb200_run_ensemble: stream_e and stream_u come together");
+    if (a->mode == KMCB200_MODE_FAST && lay->dev.S > 64)
+        return fail("kmcb200_run_ensemble: fast kernel supports N+P <= 64 in this build");
+    if (lay->dev.P > 32) return fail("kmcb200_run_ensemble: more than 32 electrodes unsupported");
+    return 0;
+}
+
+extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
+    if (validate(lay, a)) return 1;
+    if (a->B == 0) return 0;
+    std::lock_guard<std::mutex> lock(lay->mu);
+    CU(cudaSetDevice(lay->device));
+    cudaStream_t st = (cudaStream_t)a->stream;
+    const LayoutDev &D = lay->dev;
+    const int N = D.N, P = D.P, S = D.S;
+    const int64_t B = a->B, H = a->prehops + a->hops;
+    const bool dev_ptrs = a->flags & KMCB200_FLAG_DEVICE_PTRS;
+    const bool exact = a->mode != KMCB200_MODE_FAST;
+
+    EnsembleDev E{};
+    E.B = B; E.hops = a->hops; E.prehops = a->prehops; E.mode = a->mode;
+    E.seed = a->seed; E.member_index0 = a->member_index0;
+
+    // workspace sizing
+    size_t need = 0;
+    const size_t scratch_bytes = exact ? a256(sizeof(double) * (size_t)B * S * S) : 0;
+    need += scratch_bytes;
+    if (!dev_ptrs) {
+        if (a->E_constant) need += a256(sizeof(double) * B * N);
+        if (a->basis) need += a256(sizeof(double) * (size_t)(P + 1) * N);
+        if (a->electrode_v) need += a256(sizeof(double) * B * P);
+        need += a256(sizeof(double) * B);
+        if (a->occupation0) need += a256((size_t)B * N);
+        if (a->stream_e) need += a256(sizeof(double) * B * H);
+        if (a->stream_u) need += a256(sizeof(float) * B * H);
+        if (a->stream_u64) need += a256(sizeof(double) * B * 2 * H);
+        need += a256(sizeof(double) * B) + a256(sizeof(int64_t) * B * P);
+        if (a->occupation_out) need += a256((size_t)B * N);
+        if (a->site_energies_out) need += a256(sizeof(double) * B * S);
+        if (a->avg_occupation) need += a256(sizeof(double) * B * N);
+        if (a->traffic) need += a256(sizeof(double) * (size_t)B * S * S);
+        if (a->trace) need += a256(sizeof(int32_t) * (size_t)B * a->hops * 2);
+    }
+    if (need > lay->ws_bytes) {
+        if (lay->ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ws)); lay->ws = nullptr; lay->ws_bytes = 0; }
+        CU(cudaMalloc(&lay->ws, need));
+        lay->ws_bytes = need;
+    }
+    Carver cv{(char *)lay->ws};
+    if (exact) E.scratch = cv.take<double>((size_t)B * S * S);
+
+    if (dev_ptrs) {
+        E.E_constant = a->E_constant; E.basis = a->basis; E.electrode_v = a->electrode_v; E.kT = a->kT;
+        E.occupation0 = a->occupation0; E.stream_e = a->stream_e; E.stream_u = a->stream_u; E.stream_u64 = a->stream_u64;
+        E.time = a->time; E.electrode_occ = a->electrode_occ; E.occupation_out = a->occupation_out;
+        E.site_energies_out = a->site_energies_out; E.avg_occupation = a->avg_occupation; E.traffic = a->traffic;
+        E.trace = a->trace;
+        if (E.traffic) CU(cudaMemsetAsync(E.traffic, 0, sizeof(double) * (size_t)B * S * S, st));
+    } else {
+#define H2D(field, T, count)                                                                          \
+    if (a->field) {                                                                                   \
+        T *p__ = cv.take<T>(count);                                                                   \
+        CU(cudaMemcpyAsync(p__, a->field, sizeof(T) * (size_t)(count), cudaMemcpyHostToDevice, st));  \
+        E.field = p__;                                                                                \
+    }
+        H2D(E_constant, double, (size_t)B * N)
+        H2D(basis, double, (size_t)(P + 1) * N)
+        H2D(electrode_v, double, (size_t)B * P)
+        H2D(kT, double, (size_t)B)
+        H2D(occupation0, uint8_t, (size_t)B * N)
+        H2D(stream_e, double, (size_t)B * H)
+        H2D(stream_u, float, (size_t)B * H)
+        H2D(stream_u64, double, (size_t)B * 2 * H)
+#undef H2D
+        E.time = cv.take<double>(B);
+        E.electrode_occ = cv.take<int64_t>((size_t)B * P);
+        if (a->occupation_out) E.occupation_out = cv.take<uint8_t>((size_t)B * N);
+        if (a->site_energies_out) E.site_energies_out = cv.take<double>((size_t)B * S);
+        if (a->avg_occupation) E.avg_occupation = cv.take<double>((size_t)B * N);
+        if (a->traffic) {
+            E.traffic = cv.take<double>((size_t)B * S * S);
+            CU(cudaMemsetAsync(E.traffic, 0, sizeof(double) * (size_t)B * S * S, st));
+        }
+        if (a->trace) E.trace = cv.take<int32_t>((size_t)B * a->hops * 2);
+    }
+
+    int launches = 0;
+    cudaError_t le = exact ? launch_exact(D, E, st, &launches) : launch_fast(D, E, st, &launches);
+    g_launches += launches;
+    if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));
+
+    if (!dev_ptrs) {
+#define D2H(field, T, count)                                                                           \
+    if (a->field) CU(cudaMemcpyAsync(a->field, E.field, sizeof(T) * (size_t)(count), cudaMemcpyDeviceToHost, st));
+        D2H(time, double, (size_t)B)
+        D2H(electrode_occ, int64_t, (size_t)B * P)
+        D2H(occupation_out, uint8_t, (size_t)B * N)
+        D2H(site_energies_out, double, (size_t)B * S)
+        D2H(avg_occupation, double, (size_t)B * N)
+        D2H(traffic, double, (size_t)B * S * S)
+        D2H(trace, int32_t, (size_t)B * a->hops * 2)
+#undef D2H
+        CU(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+extern "C" int kmcb200_probe_rates(kmcb200_layout *lay, const double *E_constant, const double *electrode_v,
+                                   double kT, const uint8_t *occupation, float *site_energies_io,
+                                   int energies_given, float *rates_out) {
+    if (!lay || !E_constant || !occupation || !site_energies_io || !rates_out) return fail("kmcb200_probe_rates: null argument");
+    std::lock_guard<std::mutex> lock(lay->mu);
+    CU(cudaSetDevice(lay->device));
+    const int N = lay->dev.N, P = lay->dev.P, S = lay->dev.S;
+    double *dE = nullptr, *dV = nullptr; uint8_t *dO = nullptr; float *dS = nullptr, *dR = nullptr;
+    CU(cudaMalloc(&dE, sizeof(double) * (N + 1))); CU(cudaMalloc(&dV, sizeof(double) * (P + 1)));
+    CU(cudaMalloc(&dO, N + 1)); CU(cudaMalloc(&dS, sizeof(float) * S)); CU(cudaMalloc(&dR, sizeof(float) * S * S));
+    CU(cudaMemcpy(dE, E_constant, sizeof(double) * N, cudaMemcpyHostToDevice));
+    if (P) CU(cudaMemcpy(dV, electrode_v, sizeof(double) * P, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dO, occupation, N, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(dS, site_energies_io, sizeof(float) * S, cudaMemcpyHostToDevice));
+    int launches = 0;
+    cudaError_t le = launch_probe(lay->dev, dE, dV, kT, dO, dS, energies_given, dR, 0, &launches);
+    g_launches += launches;
+    if (le != cudaSuccess) return fail(std::string("probe launch: ") + cudaGetErrorString(le));
+    CU(cudaMemcpy(site_energies_io, dS, sizeof(float) * S, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rates_out, dR, sizeof(float) * S * S, cudaMemcpyDeviceToHost));
+    cudaFree(dE); cudaFree(dV); cudaFree(dO); cudaFree(dS); cudaFree(dR);
+    return 0;
+}
+
+// ---------------------------------------------------------------- Part 1: libSimulation.so exports
+namespace {
+
+// Layout cache: the reference's callers pass the same tables over and over (dn_search.py:107-118,
+// voltage_search.py:138-157); keep the device copies keyed by content.
+struct LayoutKey {
+    int N, P; double nu, I_0, R, cut; uint64_t h1, h2;
+    bool operator<(const LayoutKey &o) const { return memcmp(this, &o, sizeof(LayoutKey)) < 0; }
+};
+std::mutex g_cache_mu;
+std::map<LayoutKey, kmcb200_layout *> g_cache;
+
+uint64_t fnv(const double *p, size_t n, uint64_t h) {
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(p);
+    for (size_t i = 0; i < n * sizeof(double); ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
+    return h;
+}
+
+kmcb200_layout *cached_layout(int N, int P, const double *d, const double *tc, double nu, double I_0, double R, double cut) {
+    const size_t SS = (size_t)(N + P) * (N + P);
+    LayoutKey k;
+    memset(&k, 0, sizeof(k));
+    k.N = N; k.P = P; k.nu = nu; k.I_0 = I_0; k.R = R; k.cut = cut;
+    k.h1 = fnv(d, SS, 0xcbf29ce484222325ULL); k.h2 = fnv(tc, SS, 0x84222325cbf29ce4ULL);
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    auto it = g_cache.find(k);
+    if (it != g_cache.end()) return it->second;
+    if (g_cache.size() >= 64) {
+        for (auto &kv : g_cache) kmcb200_layout_destroy(kv.second);
+        g_cache.clear();
+    }
+    kmcb200_layout *lay = kmcb200_layout_create(0, N, P, d, tc, nu, I_0, R, cut);
+    if (lay) g_cache[k] = lay;
+    return lay;
+}
+
+[[noreturn]] void die(const char *where) {
+    // The reference has no error channel across the FFI (Go panics abort the process).
+    fprintf(stderr, "libkmcb200: %s: %s\n", where, g_err.c_str());
+    abort();
+}
+
+double run_single(const char *name, long long NSites, long long NElectrodes, double cut, double nu, double kT,
+                  double I_0, double R, GoSlice distances, GoSlice E_constant, GoSlice transitions_constant,
+                  GoSlice electrode_occupation, GoSlice site_energies, int hops, bool record, GoSlice traffic,
+                  GoSlice average_occupation) {
+    const int N = (int)NSites, P = (int)NElectrodes, S = N + P;
+    if (distances.len < (long long)S * S || transitions_constant.len < (long long)S * S || E_constant.len < N ||
+        site_energies.len < S || electrode_occupation.len < P) {
+        fail("slice shorter than NSites/NElectrodes imply");
+        die(name);
+    }
+    kmcb200_layout *lay = cached_layout(N, P, distances.data, transitions_constant.data, nu, I_0, R, cut);
+    if (!lay) die(name);
+    double time = 0.0;
+    std::vector<int64_t> eo(P > 0 ? P : 1, 0);
+    kmcb200_ensemble_args a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.hops = hops; a.prehops = 0; a.mode = KMCB200_MODE_FAST;
+    a.E_constant = E_constant.data;
+    a.electrode_v = site_energies.data + N;  // site_energies[N:] = electrode energies (kmc_dopant_networks.py:899)
+    a.kT = &kT;
+    a.occupation0 = nullptr;  // all-empty start (simulationWrapper.go:90,134-141,156-163)
+    a.seed = g_seed.load(); a.member_index0 = g_next_member.fetch_add(1);
+    a.time = &time; a.electrode_occ = eo.data();
+    if (record) {
+        if (traffic.data && traffic.len >= (long long)S * S) a.traffic = traffic.data;
+        if (average_occupation.data && average_occupation.len >= N) a.avg_occupation = average_occupation.data;
+    }
+    if (kmcb200_run_ensemble(lay, &a)) die(name);
+    for (int p = 0; p < P; ++p) electrode_occupation.data[p] = (double)eo[p];
+    return time;
+}
+}  // namespace
+
+extern "C" double wrapperSimulate(long long NSites, long long NElectrodes, double nu, double kT, double I_0, double R,
+                                  double, GoSlice, GoSlice distances, GoSlice E_constant, GoSlice transitions_constant,
+                                  GoSlice electrode_occupation, GoSlice site_energies, int hops, unsigned char record,
+                                  GoSlice traffic, GoSlice average_occupation) {
+    return run_single("wrapperSimulate", NSites, NElectrodes, 0.0, nu, kT, I_0, R, distances, E_constant,
+                      transitions_constant, electrode_occupation, site_energies, hops, record != 0, traffic, average_occupation);
+}
+extern "C" double wrapperSimulateRecord(long long NSites, long long NElectrodes, double nu, double kT, double I_0, double R,
+                                        double, GoSlice, GoSlice distances, GoSlice E_constant, GoSlice transitions_constant,
+                                        GoSlice electrode_occupation, GoSlice site_energies, int hops, unsigned char record,
+                                        GoSlice traffic, GoSlice average_occupation) {
+    // same loop as wrapperSimulate plus the state cache (simulationWrapper.go:142-144); the cache is a
+    // CPU memoisation of a pure function and is not reproduced on the GPU.
+    return run_single("wrapperSimulateRecord", NSites, NElectrodes, 0.0, nu, kT, I_0, R, distances, E_constant,
+                      transitions_constant, electrode_occupation, site_energies, hops, record != 0, traffic, average_occupation);
+}
+extern "C" double wrapperSimulateRecordPlus(long long NSites, long long NElectrodes, double nu, double kT, double I_0, double R,
+                                            double, GoSlice, GoSlice distances, GoSlice E_constant, GoSlice transitions_constant,
+                                            GoSlice electrode_occupation, GoSlice site_energies, int hops, unsigned char,
+                                            GoSlice traffic, GoSlice average_occupation) {
+    // record is forced off (simulationWrapper.go:164-165)
+    return run_single("wrapperSimulateRecordPlus", NSites, NElectrodes, 0.0, nu, kT, I_0, R, distances, E_constant,
+                      transitions_constant, electrode_occupation, site_energies, hops, false, traffic, average_occupation);
+}
+extern "C" double wrapperSimulatePruned(long long NSites, long long NElectrodes, double prune_threshold, double nu, double kT,
+                                        double I_0, double R, double, GoSlice, GoSlice distances, GoSlice E_constant,
+                                        GoSlice transitions_constant, GoSlice electrode_occupation, GoSlice site_energies,
+                                        int hops, unsigned char record, GoSlice traffic, GoSlice average_occupation) {
+    return run_single("wrapperSimulatePruned", NSites, NElectrodes, prune_threshold, nu, kT, I_0, R, distances, E_constant,
+                      transitions_constant, electrode_occupation, site_energies, hops, record != 0, traffic, average_occupation);
+}
+
+extern "C" long long parallelSimulations(GoSlice NSites, GoSlice NElectrodes, GoSlice nu, GoSlice kT, GoSlice I_0, GoSlice R,
+                                         GoSlice occupation, GoSlice distances, GoSlice E_constant,
+                                         GoSlice transitions_constant, GoSlice electrode_occupation, GoSlice hops,
+                                         GoSlice time, GoSlice site_energies) {
+    const long long B = NSites.len;
+    struct Sim { int N, P; long long hops; size_t offS, offE, offC, offSE; };
+    std::vector<Sim> sims((size_t)B);
+    size_t tS = 0, tE = 0, tC = 0;
+    for (long long i = 0; i < B; ++i) {  // running offsets as simulationWrapper.go:285-309
+        Sim &s = sims[(size_t)i];
+        s.N = (int)NSites.data[i]; s.P = (int)NElectrodes.data[i]; s.hops = (long long)hops.data[i];
+        s.offS = tS; s.offE = tE; s.offC = tC; s.offSE = tS + tE;
+        tS += s.N; tE += s.P; tC += (size_t)(s.N + s.P) * (s.N + s.P);
+    }
+    // group simulations that share a layout + hop count; each group is one ensemble launch
+    std::map<std::pair<kmcb200_layout *, long long>, std::vector<long long>> groups;
+    for (long long i = 0; i < B; ++i) {
+        const Sim &s = sims[(size_t)i];
+        kmcb200_layout *lay = cached_layout(s.N, s.P, distances.data + s.offC, transitions_constant.data + s.offC,
+                                            nu.data[i], I_0.data[i], R.data[i], 0.0);
+        if (!lay) die("parallelSimulations");
+        groups[{lay, s.hops}].push_back(i);
+    }
+    for (auto &g : groups) {
+        kmcb200_layout *lay = g.first.first;
+        const std::vector<long long> &idx = g.second;
+        const int N = lay->dev.N, P = lay->dev.P;
+        const size_t G = idx.size();
+        std::vector<double> Ec(G * N), V(G * (P ? P : 1)), kTs(G), tm(G);
+        std::vector<uint8_t> occ(G * (N ? N : 1));
+        std::vector<int64_t> eo(G * (P ? P : 1));
+        for (size_t q = 0; q < G; ++q) {
+            const Sim &s = sims[(size_t)idx[q]];
+            for (int i = 0; i < N; ++i) {
+                Ec[q * N + i] = E_constant.data[s.offS + i];
+                occ[q * N + i] = occupation.data[s.offS + i] > 0;  // honoured: simulationWrapper.go:253-260
+            }
+            for (int p = 0; p < P; ++p) V[q * P + p] = site_energies.data[s.offSE + N + p];
+            kTs[q] = kT.data[idx[q]];
+        }
+        kmcb200_ensemble_args a;
+        memset(&a, 0, sizeof(a));
+        a.B = (int64_t)G; a.hops = g.first.second; a.mode = KMCB200_MODE_FAST;
+        a.E_constant = Ec.data(); a.electrode_v = V.data(); a.kT = kTs.data(); a.occupation0 = occ.data();
+        a.seed = g_seed.load(); a.member_index0 = g_next_member.fetch_add(G);
+        a.time = tm.data(); a.electrode_occ = eo.data();
+        if (kmcb200_run_ensemble(lay, &a)) die("parallelSimulations");
+        for (size_t q = 0; q < G; ++q) {
+            const Sim &s = sims[(size_t)idx[q]];
+            time.data[idx[q]] = tm[q];
+            for (int p = 0; p < P; ++p) electrode_occupation.data[s.offE + p] = (double)eo[q * P + p];
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,45 @@
+// kmc_internal.cuh -- shared declarations between the C-ABI host code and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kmcb200 {
+
+// Device-resident tables of one layout (built once by kmcb200_layout_create).
+struct LayoutDev {
+    int N, P, S;
+    int slots;      // ceil(S/32): row slots per lane in the fast kernel
+    int pitch2;     // fast-table row pitch in float2 units (= 32*slots + 1, bank-conflict-free both ways)
+    // fast table: tbl[j*pitch2 + i] = { nu*tc[i][j] (0 if pruned / diagonal / electrode-electrode),
+    //                                   I_0*R/d[i][j] for acceptor-acceptor pairs i!=j, else 0 }
+    // i.e. indexed [target j][source i]; fp32 narrowing as simulationWrapper.go:37-56.
+    float2 *tbl;
+    // replay tables (row-major, exactly the caller's values)
+    float *d32, *tc32;       // [S*S] narrowed (Go semantics)
+    double *d64, *tc64;      // [S*S] (numba semantics)
+    int2 *pairs;             // Go transition list (simulation.go:199-215), length L
+    int L;
+    float nu32, I032, R32;   // narrowed scalars (simulationWrapper.go:92)
+    double nu64, I064, R64;
+};
+
+struct EnsembleDev {
+    int64_t B, hops, prehops;
+    int mode;
+    const double *E_constant, *basis, *electrode_v, *kT;
+    const uint8_t *occupation0;
+    uint64_t seed, member_index0;
+    const double *stream_e; const float *stream_u; const double *stream_u64;
+    double *time; int64_t *electrode_occ; uint8_t *occupation_out; double *site_energies_out;
+    double *avg_occupation; double *traffic; int32_t *trace;
+    double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
+};
+
+// launchers (return cudaError_t of the launch)
+cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
+cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
+cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,
+                         const uint8_t *occ, float *se_io, int se_given, float *rates_out, cudaStream_t st,
+                         int *launches);
+
+}  // namespace kmcb200
