@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- aggregate KMC hops/s of the B200 hop loop on BASELINE.json's voltage-search ensemble (C3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hops H]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one pass of the hop loop over the whole ensemble (n_controls x 4 inputs x seeds members,
+each `hops` hops).  Ensemble members are sharded over ranks in contiguous blocks with global Philox
+stream numbering (weak scaling: every GPU gets a full C3 ensemble); the only collective is the final
+NCCL all_gather of the time / electrode tallies.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "aggregate KMC hops/s over ensemble"
+UNIT = "hops/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hops", type=int, default=10000, help="hops per member per step")
+    ap.add_argument("--controls", type=int, default=16384, help="control-voltage vectors (x4 inputs x seeds members)")
+    ap.add_argument("--seeds", type=int, default=16)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    from kmc_dn_b200 import workloads
+    return workloads.c3_voltage_search(n_controls=args.controls, seeds=args.seeds, hops=args.hops)
+
+
+def config_of(args, w, n_gpus):
+    return {"workload": "C3 boolean_logic/voltage_search: reference layout 0 (30 acceptors, 3 donors), 8 electrodes, "
+                        f"{args.controls} control vectors x 4 inputs x {args.seeds} seeds = {len(w['V'])} members per GPU, "
+                        f"{args.hops} hops per member per step",
+            "members_per_gpu": int(len(w["V"])), "hops_per_member": int(args.hops), "N": 30, "P": 8,
+            "parallelism": f"ensemble-sharded x{n_gpus} (no data-path collective; final NCCL all_gather of tallies)",
+            "l2": "flushed between timed steps (256 MiB write)", "rng": "Philox4x32-10 (seed, global member index)"}
+
+
+# ---------------------------------------------------------------------------------------- CPU arms
+def cpu_sample(w, seconds, variant=1, use_cache=True, semantics="go", nthreads=0):
+    """Times the oracle on a bounded sample of the same workload on all host cores."""
+    from oracle import oracle
+    lt = w["tables"]
+    cores = os.cpu_count() or 1
+    nthreads = nthreads or cores
+
+    def run(B, hops):
+        V = w["V"][:: max(1, len(w["V"]) // B)][:B]
+        E = lt.E_constant(V)
+        t0 = time.perf_counter()
+        if semantics == "go":
+            r = oracle.go_ensemble(lt.N, lt.P, lt.nu, 1.0, lt.I_0, lt.R, lt.distances, E, lt.transitions_constant, V, hops,
+                                   variant=variant, use_cache=use_cache, occupation0=w["occupation0"], seed0=1,
+                                   nthreads=nthreads)
+        else:
+            r = oracle.py_ensemble(lt.N, lt.P, lt.nu, 1.0, lt.I_0, lt.R, lt.distances, E, lt.transitions_constant, V, hops,
+                                   occupation0=w["occupation0"], seed0=1, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        return B * hops / dt, dt, r["threads"]
+
+    hops = w["hops"]
+    B0 = 2 * nthreads
+    rate, dt, used = run(B0, min(hops, 2000))           # calibration
+    B = int(max(B0, min(len(w["V"]), (rate * seconds) // hops // nthreads * nthreads)))
+    rate, dt, used = run(B, hops)
+    return dict(value=rate, seconds=dt, cores=used, members=B, hops=hops)
+
+
+def reference_arm(args):
+    """--impl reference: the reference's CPU path for this workload (the C restatement of the Go loop the
+    reference's batched API runs: parallelSimulations -> simulateRecordPlus with its state cache,
+    simulationWrapper.go:274-316) on all host cores; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(args)
+    per_step = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(w, per_step / 4)
+    vals = []
+    t_all = 0.0
+    for _ in range(args.steps):
+        s = cpu_sample(w, per_step)
+        vals.append(s)
+        t_all += s["seconds"]
+    total_hops = sum(s["members"] * s["hops"] for s in vals)
+    value = total_hops / t_all
+    s0 = vals[-1]
+    sample = f"{s0['members']} members x {s0['hops']} hops per step (members strided out of the full ensemble)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_all / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 rates / f64 time", "data": "synthetic",
+            "config": config_of(args, w, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": s0["cores"], "kind": "port", "sample": sample,
+                             "what": "C restatement of goSimulation simulateRecordPlus + state cache (Go toolchain "
+                                     "unavailable), one trajectory per thread"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------- our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from kmc_dn_b200.ensemble import Layout, launch_count
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workload(args)
+    lt = w["tables"]
+    B = len(w["V"])
+    hops = args.hops
+    lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R, device=local)
+    member0 = rank * B  # global numbering: every rank holds a full C3 ensemble with its own Philox streams
+
+    # ---- device-resident inputs (value leg) and pinned host buffers (e2e leg)
+    V_h = torch.from_numpy(np.ascontiguousarray(w["V"])).pin_memory()
+    kT_h = torch.from_numpy(np.ascontiguousarray(w["kT"])).pin_memory()
+    occ_h = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(w["occupation0"], (B, lt.N)).astype(np.uint8))).pin_memory()
+    basis_h = torch.from_numpy(np.ascontiguousarray(lt.basis)).pin_memory()
+    V_d, kT_d, occ_d, basis_d = V_h.to(dev), kT_h.to(dev), occ_h.to(dev), basis_h.to(dev)
+    time_d = torch.zeros(B, dtype=torch.float64, device=dev)
+    eo_d = torch.zeros((B, lt.P), dtype=torch.int64, device=dev)
+    time_out = torch.zeros(B, dtype=torch.float64).pin_memory()
+    eo_out = torch.zeros((B, lt.P), dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gather_t = [torch.empty_like(time_d) for _ in range(world)] if world > 1 else None
+    gather_e = [torch.empty_like(eo_d) for _ in range(world)] if world > 1 else None
+    stream = torch.cuda.current_stream()
+
+    def step_device(i):
+        lay.run_device(B, hops, kT_d, V_d, time_d, eo_d, basis=basis_d, occupation0=occ_d, seed=1000 + i,
+                       member_index0=member0, cuda_stream=stream.cuda_stream)
+        if world > 1:  # the path's only exchange: gather the tallies
+            dist.all_gather(gather_t, time_d)
+            dist.all_gather(gather_e, eo_d)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local); sampler.start()
+    l0 = launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xff)
+        ev[i][0].record(stream)
+        step_device(100 + i)
+        ev[i][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = launch_count() - l0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop()
+    tsum = float(time_d.sum().item())
+    assert np.isfinite(tsum) and tsum > 0, "kernel produced no valid times"
+
+    # ---- e2e: the public host API (pinned host buffers in, host results out), copies inside the timed region
+    Vn, kTn, occn, bn = V_h.numpy(), kT_h.numpy(), occ_h.numpy(), basis_h.numpy()
+
+    def step_e2e(i):
+        a = lay_run_host(lay, B, hops, kTn, Vn, bn, occn, time_out, eo_out, 2000 + i, member0, stream.cuda_stream)
+        if world > 1:
+            dist.all_gather(gather_t, time_d)
+        return a
+
+    for i in range(min(2, args.warmup)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(10 + i)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # ---- max over ranks
+    t = torch.tensor([ms, t_e2e * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    hops_per_step_all = float(B) * hops * world
+    value = hops_per_step_all * args.steps / (ms * 1e-3)
+    e2e_value = hops_per_step_all * args.steps / (e2e_ms * 1e-3)
+    h2d = V_h.numel() * 8 + kT_h.numel() * 8 + occ_h.numel() + basis_h.numel() * 8
+    d2h = time_out.numel() * 8 + eo_out.numel() * 8
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 rates / f64 cumulative+time", "data": "synthetic", "config": config_of(args, w, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall}
+        line["roofline"] = roofline(value / world, ms / args.steps, B, hops, lt, clocks)
+        if world == 1 and not args.no_cpu_baseline:
+            s = cpu_sample(w, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": s["value"], "unit": UNIT, "cores": s["cores"], "kind": "port",
+                                    "sample": f"{s['members']} members x {s['hops']} hops (strided subset of the same "
+                                              f"ensemble), {s['seconds']:.1f} s",
+                                    "what": "C restatement of simulateRecordPlus + state cache (what parallelSimulations runs)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def lay_run_host(lay, B, hops, kT, V, basis, occ0, time_out, eo_out, seed, member0, cuda_stream):
+    """Host-pointer call of the C ABI with caller-owned pinned buffers (what kmc_dn_b200.ensemble.Layout.run does,
+    minus the per-call numpy allocations)."""
+    import ctypes as C
+    from kmc_dn_b200 import _lib
+    a = _lib.EnsembleArgs()
+    a.B, a.hops, a.prehops, a.mode, a.flags = B, hops, 0, 0, 0
+    a.basis, a.electrode_v, a.kT, a.occupation0 = basis.ctypes.data, V.ctypes.data, kT.ctypes.data, occ0.ctypes.data
+    a.seed, a.member_index0 = seed, member0
+    a.time, a.electrode_occ = time_out.data_ptr(), eo_out.data_ptr()
+    a.stream = cuda_stream
+    if lay.lib.kmcb200_run_ensemble(lay._h, C.byref(a)):
+        raise RuntimeError(_lib.last_error())
+
+
+def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, clocks):
+    """The hop loop is neither HBM- nor tensor-bound.  `achieved` is stated against HBM as the
+    contract asks (it is ~0 by construction); the informative fractions are in `pipes`."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    S = lt.S
+    table_bytes = S * (32 * ((S + 31) // 32) + 1) * 8
+    bytes_per_member = 8 * lt.P + 8 + lt.N + 8 + 8 * lt.P + table_bytes / 8.0  # inputs + outputs + table share (8 warps/CTA)
+    algo_bytes = B * bytes_per_member
+    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "traffic": None,
+            "note": "latency/issue-bound persistent loop: HBM traffic is O(inputs+outputs) once per launch"}
+
+
+if __name__ == "__main__":
+    main()

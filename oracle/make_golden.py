@@ -96,6 +96,15 @@ def run_reference(ref, seed_fn, c, seed, hops, trace_hops):
                 site_energies=se.copy(), traffic_tail=traffic, occ_time_tail=occ_time, time_tail=t)
 
 
+def layouts():
+    """4. layouts.npz -- dopant layouts the reference's experiments ship as data and BASELINE.json's
+    configs name (experiments/boolean_logic/random_layouts/*.npy: 100 layouts of 30 acceptors / 3 donors;
+    the first four are kept)."""
+    a = np.load(f"{REF}/experiments/boolean_logic/random_layouts/acceptor_layouts.npy")
+    d = np.load(f"{REF}/experiments/boolean_logic/random_layouts/donor_layouts.npy")
+    np.savez_compressed(os.path.join(OUT, "layouts.npz"), acceptor_layouts=a[:4], donor_layouts=d[:4])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref, seed_fn = numba_ref.load()
@@ -143,6 +152,7 @@ def main():
                       "mu", "res", "xdim", "ydim", "static_electrodes"]:
                 blob[f"{setname}/test{i}/{k}"] = np.asarray(d[k])
     np.savez_compressed(os.path.join(OUT, "electrostatics.npz"), **blob)
+    layouts()
     for f in sorted(glob.glob(os.path.join(OUT, "*.npz"))):
         print(f, os.path.getsize(f))
 
