@@ -89,6 +89,7 @@ class BasisPotentials:
         t = acceptors[:, 0] / xdim
         phi[ends[0]] += 1.0 - t
         phi[ends[1]] += t
+        self._grid = ("1d", ends, xdim, K)
         return phi
 
     def _solve_2d(self, acceptors, electrodes, static_electrodes, xdim, ydim, res):
@@ -124,20 +125,39 @@ class BasisPotentials:
         for k in range(K + 1):
             U[k][interior] = sol[:, k]
             U[k][owner == (-1 if k == K else k)] = 1.0
-        # P1 interpolation, cells split along the "right" diagonal (DOLFIN RectangleMesh default)
+        self._grid = ("2d", xs, ys, hx, hy, U)
         phi = np.zeros((K + 1, self.N))
         for a in range(self.N):
-            x, y = acceptors[a, 0], acceptors[a, 1]
-            cx = min(max(int(np.floor(x / hx)), 0), nx - 1)
-            cy = min(max(int(np.floor(y / hy)), 0), ny - 1)
-            s = (x - xs[cx]) / hx
-            t = (y - ys[cy]) / hy
-            v00, v10, v01, v11 = U[:, cx, cy], U[:, cx + 1, cy], U[:, cx, cy + 1], U[:, cx + 1, cy + 1]
-            if s >= t:
-                phi[:, a] = v00 + s * (v10 - v00) + t * (v11 - v10)
-            else:
-                phi[:, a] = v00 + t * (v01 - v00) + s * (v11 - v01)
+            phi[:, a] = self.basis_at(acceptors[a, 0], acceptors[a, 1])
         return phi
+
+    def basis_at(self, x, y=0.0):
+        """All basis potentials at an arbitrary point: P1 interpolation, cells split along the "right"
+        diagonal (bottom-left -> top-right, DOLFIN's RectangleMesh default)."""
+        if self._grid[0] == "1d":
+            _, ends, xdim, K = self._grid
+            out = np.zeros(K + 1)
+            out[ends[0]] += 1.0 - x / xdim
+            out[ends[1]] += x / xdim
+            return out
+        _, xs, ys, hx, hy, U = self._grid
+        nx, ny = len(xs) - 1, len(ys) - 1
+        cx = min(max(int(np.floor(x / hx)), 0), nx - 1)
+        cy = min(max(int(np.floor(y / hy)), 0), ny - 1)
+        s = (x - xs[cx]) / hx
+        t = (y - ys[cy]) / hy
+        v00, v10, v01, v11 = U[:, cx, cy], U[:, cx + 1, cy], U[:, cx, cy + 1], U[:, cx + 1, cy + 1]
+        if s >= t:
+            return v00 + s * (v10 - v00) + t * (v11 - v10)
+        return v00 + t * (v01 - v00) + s * (v11 - v01)
+
+    def potential_at(self, x, y, electrode_v, mu=0.0, static_v=None):
+        """V(x,y) for given electrode voltages -- what the reference's FEniCS function object returns."""
+        b = self.basis_at(x, y)
+        v = float(np.dot(np.asarray(electrode_v, dtype=np.float64), b[:self.P]) + mu * b[-1])
+        if self.n_static:
+            v += float(np.dot(np.asarray(static_v, dtype=np.float64), b[self.P:self.P + self.n_static]))
+        return v
 
     # ------------------------------------------------------------------
     def eV_constant(self, electrode_v, mu=0.0, static_v=None):

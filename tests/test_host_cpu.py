@@ -1,0 +1,123 @@
+"""CPU suite, part 2: electrostatics front end and the kmc_dn host class set-up against the reference's
+stored fixture fields (inputs pinned to fp64 round-off), plus the benchmark workload builders."""
+import numpy as np
+import pytest
+
+from tests.util import load_cases
+
+
+@pytest.fixture(scope="module")
+def estat():
+    return load_cases("electrostatics.npz")
+
+
+def test_basis_potentials_reproduce_fenics_eV_constant(estat):
+    """Superposition of per-electrode FD/P1 solutions == the FEniCS solve stored in the reference's fixtures
+    (kmc_dopant_networks.py:706-899).  40 fixtures, |error| <= 2e-11 on values of magnitude ~100."""
+    from kmc_dn_b200.electrostatics import BasisPotentials, comp_constant
+    assert len(estat) == 40
+    by_layout = {}
+    for name, c in estat.items():
+        key = (c["acceptors"].tobytes(), c["electrodes"][:, :3].tobytes())
+        if key not in by_layout:
+            by_layout[key] = BasisPotentials(c["acceptors"], c["electrodes"], float(c["xdim"]), float(c["ydim"]), 0.0,
+                                             res=float(c["res"]))
+        bp = by_layout[key]
+        ev = bp.eV_constant(c["electrodes"][:, 3], mu=float(c["mu"]))
+        np.testing.assert_allclose(ev, c["eV_constant"], rtol=0, atol=2e-11, err_msg=name)
+        cc = comp_constant(c["acceptors"], c["donors"], float(c["I_0"]), float(c["R"]))
+        np.testing.assert_allclose(cc, c["comp_constant"], rtol=1e-14, err_msg=name)
+        basis = bp.kernel_basis(cc, mu=float(c["mu"]))
+        np.testing.assert_allclose(c["electrodes"][:, 3] @ basis[:-1] + basis[-1], c["E_constant"], rtol=0, atol=2e-11)
+    assert len(by_layout) < len(estat)  # XOR fixtures share layouts: one factorisation serves many voltage vectors
+
+
+def test_basis_potentials_partition_of_unity_and_boundary_rule(estat):
+    from kmc_dn_b200.electrostatics import BasisPotentials
+    c = estat["rnd_min_max/test0"]
+    bp = BasisPotentials(c["acceptors"], c["electrodes"], 1.0, 1.0, 0.0, res=0.01)
+    np.testing.assert_allclose(bp.phi.sum(0), 1.0, atol=1e-12)  # all boundaries at 1 -> V == 1 everywhere
+    V = c["electrodes"][:, 3]
+    for e in c["electrodes"]:  # on an electrode's centre the potential is the electrode voltage
+        assert bp.potential_at(e[0], e[1], V) == pytest.approx(e[3], abs=1e-12)
+    assert bp.potential_at(0.0, 0.5, V, mu=3.0) == pytest.approx(3.0)  # bare boundary sits at mu (:763)
+    # electrode modelled as point +- xdim/10 (:742-752): 0.34 is inside electrode 0's segment, 0.36 is not
+    assert bp.potential_at(0.0, 0.34, V) == pytest.approx(c["electrodes"][0, 3])
+    assert abs(bp.potential_at(0.0, 0.36, V)) < abs(c["electrodes"][0, 3])
+
+
+def test_one_dimensional_potential_is_linear():
+    """dim 1 (validation/set/set.py set-up): only the two end points are Dirichlet nodes (:736-739, :772)."""
+    from kmc_dn_b200.electrostatics import BasisPotentials
+    acc = np.array([[0.5, 0, 0], [0.2, 0, 0]])
+    el = np.array([[0.0, 0, 0, 4.0], [1.0, 0, 0, -2.0]])
+    bp = BasisPotentials(acc, el, 1.0)
+    np.testing.assert_allclose(bp.eV_constant(el[:, 3]), [1.0, 2.8])
+    with pytest.raises(NotImplementedError):
+        BasisPotentials(acc, el, 1.0, 1.0, 1.0)
+
+
+def test_kmc_dn_setup_matches_fixture_fields(fixtures_subset):
+    """kmc_dn built from a fixture's acceptors/donors/electrodes reproduces the stored distances,
+    transitions_constant, comp_constant, eV_constant, E_constant and R/ab."""
+    from kmc_dn_b200.kmc_dopant_networks import kmc_dn
+    for name in ("rnd_min_max/test1", "XOR_wide/test2"):
+        f = fixtures_subset[name]
+        dn = kmc_dn(int(f["N"]), int(f["M"]), 1, 1, 0, electrodes=f["electrodes"], acceptors=f["acceptors"],
+                    donors=f["donors"])
+        assert dn.R == f["R"] and dn.ab == f["ab"] and dn.P == 8 and dn.dim == 2 and dn.res == f["res"]
+        np.testing.assert_array_equal(dn.distances, f["distances"])
+        np.testing.assert_allclose(dn.transitions_constant, f["transitions_constant"], rtol=0, atol=2e-16)
+        np.testing.assert_allclose(dn.comp_constant, f["comp_constant"], rtol=1e-14)
+        np.testing.assert_allclose(dn.eV_constant, f["eV_constant"], rtol=0, atol=2e-11)
+        np.testing.assert_allclose(dn.E_constant, f["E_constant"], rtol=0, atol=2e-11)
+        np.testing.assert_array_equal(dn.site_energies[dn.N:], f["electrodes"][:, 3])
+        # update_V after a voltage change == superposition
+        dn.electrodes[:, 3] *= 0.5
+        dn.update_V()
+        np.testing.assert_allclose(dn.eV_constant, 0.5 * f["eV_constant"], rtol=0, atol=2e-11)
+        assert dn.V(dn.acceptors[3, 0], dn.acceptors[3, 1]) == pytest.approx(dn.eV_constant[3], abs=1e-12)
+
+
+def test_kmc_dn_random_placement_and_persistence(tmp_path):
+    from kmc_dn_b200.kmc_dopant_networks import kmc_dn
+    np.random.seed(3)
+    el = np.zeros((2, 4)); el[0] = [0, 0.5, 0, 10]; el[1] = [1, 0.5, 0, -10]
+    dn = kmc_dn(10, 2, 1, 1, 0, electrodes=el)
+    assert dn.occupation.sum() == 8 and dn.acceptors.shape == (10, 3) and (dn.acceptors[:, 2] == 0).all()
+    assert dn.vectors.shape == (12, 12, 3)
+    np.testing.assert_allclose(np.linalg.norm(dn.vectors[0, 1]), 1.0)
+    np.testing.assert_allclose(dn.vectors[0, 1], -dn.vectors[1, 0])
+    H = dn.total_energy()
+    assert np.isfinite(H)
+    dn.current = np.array([1.0, -1.0])
+    p = tmp_path / "x.kmc"
+    dn.saveSelf(str(p))
+    dn2 = kmc_dn(10, 2, 1, 1, 0, electrodes=el)
+    dn2.loadSelf(str(p))
+    np.testing.assert_array_equal(dn2.acceptors, dn.acceptors)
+    np.testing.assert_array_equal(dn2.E_constant, dn.E_constant)
+    np.testing.assert_array_equal(dn2.expected_current, [1.0, -1.0])
+    assert not dn2.occupation.any()  # like the reference: loadSelf re-initialises, occupation restarts empty (:978, :434)
+    dn3 = kmc_dn(10, 2, 1, 1, 0, electrodes=el, copy_from=dn)
+    assert dn3.I_0 == dn.I_0
+    dn.load_donors(np.random.rand(3, 3) * [1, 1, 0])
+    assert dn.M == 3 and dn.comp_constant.shape == (10,) and dn.occupation.sum() == 7
+
+
+def test_workload_builders_are_deterministic_and_shaped():
+    from kmc_dn_b200 import workloads
+    w = workloads.c3_voltage_search(n_controls=8, seeds=2, hops=100)
+    lt = w["tables"]
+    assert (lt.N, lt.M, lt.P) == (30, 3, 8) and w["V"].shape == (64, 8)
+    assert (w["V"][:, 7] == 0).all() and set(np.unique(w["V"][:, :2])) == {0.0, 75.0}
+    assert (w["V"][0] == w["V"][1]).all() and not (w["V"][0] == w["V"][2]).all()  # seeds are the fastest index
+    assert np.abs(w["V"][:, 2:7]).max() <= 150 and w["occupation0"].sum() == 27
+    w2 = workloads.c3_voltage_search(n_controls=8, seeds=2, hops=100)
+    np.testing.assert_array_equal(w["V"], w2["V"])
+    np.testing.assert_allclose(lt.E_constant(w["V"][:3]), w["V"][:3] @ lt.basis[:8] + lt.basis[8])
+    for f, shape in ((workloads.c1_basic, (10, 2)), (workloads.c2_grid4x4, (16, 8)), (workloads.c4_temperature, (30, 2))):
+        w = f()
+        assert (w["tables"].N, w["tables"].P) == shape and len(w["V"]) == len(w["kT"])
+    w = workloads.c5_scaling(N=64, M=6, B=16)
+    assert w["tables"].S == 72
