@@ -101,7 +101,9 @@ enum {
                                        fp64 cumulative rates + time, Philox4x32-10                      */
     KMCB200_MODE_GO_SIMULATE = 1,   /* replay: op-for-op simulate,           simulation.go:194-325     */
     KMCB200_MODE_GO_RECORDPLUS = 2, /* replay: op-for-op simulateRecordPlus, simulation.go:327-432     */
-    KMCB200_MODE_PY = 3             /* replay: op-for-op numba loop, kmc_dopant_networks.py:33-135     */
+    KMCB200_MODE_PY = 3,            /* replay: op-for-op numba loop, kmc_dopant_networks.py:33-135     */
+    KMCB200_MODE_FAST_REFORDER = 4  /* production arithmetic with the reference's row-major event order:
+                                       follows the Go loop hop for hop under an injected stream           */
 };
 
 enum {

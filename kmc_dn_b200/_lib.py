@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libkmcb200.so")
 
-MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY = 0, 1, 2, 3
+MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER = 0, 1, 2, 3, 4
 FLAG_DEVICE_PTRS = 1
 
 

@@ -1,109 +1,110 @@
-// hop_fast.cu -- production KMC hop loop for sm_100a.  One warp = one trajectory.
+// hop_fast.cu -- production KMC hop loop for sm_100a (KMCB200_MODE_FAST).  One warp = one trajectory.
 //
 // Reference semantics being accelerated (MUTUEL/kmc_dn, paths relative to the reference tree):
 //   site energies      goSimulation/simulation.go:226-234  (E_const - I0*R*sum_{j empty} 1/d_ij)
 //   incremental update goSimulation/simulation.go:107-130  (makeJump)
 //   allowed pairs      goSimulation/simulation.go:40-55
 //   Miller-Abrahams    goSimulation/simulation.go:58-80
-//   cumulative list    goSimulation/simulation.go:267-276  (row-major (from,to) order -- kept here)
+//   cumulative list    goSimulation/simulation.go:267-276
 //   dwell time / pick  goSimulation/simulation.go:297-299, 163-188
 //   tallies            goSimulation/simulation.go:306-319
 //
-// B200 design:
-//   * rows of the rate matrix (the "from" sites) live on lanes: lane l owns rows l, l+32, ...
-//     Only ALLOWED targets are visited: the empty acceptors (bit-loop over the warp-uniform
-//     occupation mask) and the electrodes.  Disallowed pairs are never evaluated.
-//   * layout table in shared memory, shared by all warps of the CTA, indexed [target][source]
-//     as float2 {nu*tc, I0*R/d}; pitch 32*SLOTS+1 float2 => conflict-free for both the
-//     row-parallel sweep and the column-parallel second-level pick.
-//   * site energies: fp64 master copy per row, updated incrementally by +-(double)kd32 -- sums
-//     of fp32 values in fp64 are exact here, so the incremental energy equals the from-scratch
-//     energy (no drift, unlike simulation.go:113,124); rounded once per hop to fp32 for the rates.
-//   * rates fp32 with MUFU.EX2; row sums fp32; prefix over rows, event pick and elapsed time fp64.
-//   * two-level pick: warp-shuffle inclusive scan over row sums -> row, then the row's targets
-//     are re-evaluated lane-parallel and scanned -> column.  Row-major order == reference order.
-//   * Philox4x32-10, counter = (64-hop block, lane | member), key = seed: one call per lane
-//     yields the two 32-bit variates of 64 hops for the whole warp.
+// B200 design.  The v1 kernel (hop_reforder.cu) was issue-bound at 589
+// warp-instructions per hop (profiles/ncu_fast_r01_v1_details.txt); this one does the same physics in
+// roughly a third of that:
+//   * lanes own ACCEPTORS only (lane l <-> acceptor l, l+32, ...).  Every allowed pair is evaluated exactly
+//     once per hop and nothing else is:
+//       - acceptor->acceptor: warp-uniform bit-loop over the EMPTY sites j; lane i (occupied) evaluates i->j;
+//       - acceptor<->electrode: loop over electrodes e; lane i evaluates i->e if it is occupied and e->i if it
+//         is empty (exactly one of the two directions is allowed for every (i,e)), so all lanes work.
+//     The event order of the cumulative list is therefore lane-major instead of the reference's row-major
+//     (electrode->acceptor events sit in the acceptor's lane).  Any fixed order samples the same Markov
+//     chain; the row-major variant is kept in hop_reforder.cu for lock-step replay against the oracle.
+//   * energies are carried pre-scaled, s = eps * (-log2e/kT), so a rate is
+//         tc * exp2(min(0, s_to - s_from + kd*log2e/kT))   =  FADD, FFMA, FMNMX, MUFU.EX2, FFMA.
+//     Rows that may not act as a source carry s_from = +1e30 instead of a predicate.
+//   * table in shared memory, [target][source] float2: {nu*tc(i->j), I0*R/d_ij} for acceptor targets,
+//     {nu*tc(i->e), nu*tc(e->i)} for electrode targets; pitch 32*AS+1 float2 (conflict-free row- and
+//     column-wise).  fp32 narrowing as the cgo wrappers do (simulationWrapper.go:37-56).
+//   * energies: fp64 master per acceptor, updated by +-(double)kd32.  Sums of fp32 values in fp64 are exact
+//     here, so the incremental energy equals the from-scratch energy bit for bit (no drift, unlike
+//     simulation.go:113,124) and the rate list is a pure function of the occupation.
+//   * rates and within-lane sums fp32; prefix over lanes, event threshold and elapsed time fp64.
+//   * two-level pick: fp64 warp-shuffle scan over lane sums -> lane; the lane's targets are re-evaluated
+//     lane-parallel and scanned (fp32) -> target.
+//   * Philox4x32-10, counter = (64-hop block | lane, member), key = seed.  Once per 64 hops every lane turns
+//     one Philox call into two (unit-exponential, 32-bit uniform) pairs and parks them in shared memory, so
+//     the per-hop cost of the generator and of the logarithm is one broadcast LDS.64.
+#include "kmc_device.cuh"
 #include "kmc_internal.cuh"
 
 namespace kmcb200 {
 
-#define FULL 0xffffffffu
+#define BIGS 1.0e30f
 
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
-__device__ __forceinline__ double warp_incl_scan(double v, int lane) {
+__device__ __forceinline__ float warp_incl_scan_f(float v, int lane) {
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const double t = __shfl_up_sync(FULL, v, d);
+        const float t = __shfl_up_sync(FULL, v, d);
         if (lane >= d) v += t;
     }
     return v;
 }
 
-// Miller-Abrahams rate of one pair: v = {nu*tc, I0*R/d (0 unless acceptor-acceptor)}.
-// dE>0 -> exp(-dE/kT), else 1   ==   exp2(min(-dE*log2e/kT, 0)).
-__device__ __forceinline__ float ma_rate(float2 v, float e_to, float e_from, float negbeta) {
-    const float dE = (e_to - e_from) - v.y;
-    return v.x * ex2_approx(fminf(dE * negbeta, 0.0f));
+// first lane whose inclusive prefix reaches thr among lanes with a positive rate; if rounding put thr past
+// the end, the last positive lane; -1 if the group is empty.
+__device__ __forceinline__ int pick_in_group(float rr, float thr, int lane) {
+    const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+    if (!nz) return -1;
+    const float s = warp_incl_scan_f(rr, lane);
+    const uint32_t bal = __ballot_sync(FULL, s >= thr) & nz;
+    return bal ? (__ffs(bal) - 1) : (31 - __clz(nz));
 }
 
-template <int SLOTS, bool RECORD>
+template <int AS, int PT, bool DBG>
 __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const EnsembleDev E) {
+    constexpr int PITCH = 32 * AS + 1;
+    constexpr int MIRW = 32 * AS + 32;  // per-warp mirror: acceptor energies [0,32*AS), electrode energies after
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *tbl = reinterpret_cast<float2 *>(smem_raw);
-    const int N = L.N, P = L.P, S = L.S, pitch2 = L.pitch2;
-    float *eps_base = reinterpret_cast<float *>(tbl + S * pitch2);
+    const int N = L.N, S = L.S;
+    const int P = PT > 0 ? PT : L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    float *mir_base = reinterpret_cast<float *>(tbl + S * PITCH);
+    uint2 *rng_base = reinterpret_cast<uint2 *>(mir_base + nwarps * MIRW);
 
-    for (int idx = tid; idx < S * pitch2; idx += blockDim.x) tbl[idx] = L.tbl[idx];
+    for (int idx = tid; idx < S * PITCH; idx += blockDim.x) tbl[idx] = L.tblf[idx];
     __syncthreads();
 
     const int64_t m = (int64_t)blockIdx.x * nwarps + warp;
     if (m >= E.B) return;
-    float *eps = eps_base + warp * (32 * SLOTS);
+    float *mir = mir_base + warp * MIRW;
+    uint2 *rngbuf = rng_base + warp * 64;
 
-    // ---- static masks per row slot
-    uint32_t accm[SLOTS], elm[SLOTS], occ[SLOTS];
+    // ---- static masks
+    uint32_t accm[AS], occ[AS];
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
+    for (int k = 0; k < AS; ++k) {
         const int lo = 32 * k;
         accm[k] = (N >= lo + 32) ? ~0u : (N > lo ? ((1u << (N - lo)) - 1u) : 0u);
-        const uint32_t sm = (S >= lo + 32) ? ~0u : (S > lo ? ((1u << (S - lo)) - 1u) : 0u);
-        elm[k] = sm & ~accm[k];
+    }
+
+    // ---- member parameters
+    const float kT = (float)E.kT[m];
+    const float nb = -1.4426950408889634f / kT;  // energies are carried as s = eps*nb
+    const float pb = -nb;
+    float se_reg[PT > 0 ? PT : 1];
+    if (lane < P) mir[32 * AS + lane] = (float)E.electrode_v[m * P + lane] * nb;
+    __syncwarp();
+    if (PT > 0) {
+#pragma unroll
+        for (int e = 0; e < (PT > 0 ? PT : 1); ++e) se_reg[e] = mir[32 * AS + e];
     }
 
     // ---- initial state: occupation, E_constant (optionally by superposition), energies
-    double eps64[SLOTS];
-    float eps32[SLOTS];
+    double eps64[AS];
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
+    for (int k = 0; k < AS; ++k) {
         const int i = lane + 32 * k;
         bool o = false;
         double e0 = 0.0;
@@ -115,94 +116,118 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
                 for (int p = 0; p < P; ++p) e0 += E.electrode_v[m * P + p] * E.basis[(int64_t)p * N + i];
             }
             e0 = (double)(float)e0;  // simulationWrapper.go:50-56 narrows E_constant to float32
-        } else if (i < S) {
-            e0 = (double)(float)E.electrode_v[m * P + (i - N)];
         }
         occ[k] = __ballot_sync(FULL, o);
         eps64[k] = e0;
     }
 #pragma unroll
-    for (int kw = 0; kw < SLOTS; ++kw) {
+    for (int kw = 0; kw < AS; ++kw) {
         uint32_t mm = ~occ[kw] & accm[kw];
         while (mm) {
             const int j = kw * 32 + __ffs(mm) - 1;
             mm &= mm - 1;
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k) eps64[k] -= (double)tbl[j * pitch2 + lane + 32 * k].y;
+            for (int k = 0; k < AS; ++k) eps64[k] -= (double)tbl[j * PITCH + lane + 32 * k].y;
         }
     }
 
-    const float negbeta = -1.4426950408889634f / (float)E.kT[m];
     const uint64_t gm = E.member_index0 + (uint64_t)m;
     const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
-    const bool inject = E.stream_e != nullptr;
+    const bool inject = DBG && E.stream_e != nullptr;
     const int64_t total_hops = E.prehops + E.hops;
 
-    uint4 rnd = make_uint4(0, 0, 0, 0);
     double t_acc = 0.0;
+    float t_part = 0.0f;
     int eoc = 0;
-    double occtime[SLOTS];
+    double occtime[AS];
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) occtime[k] = 0.0;
+    for (int k = 0; k < AS; ++k) occtime[k] = 0.0;
     bool dead = false;
 
     for (int64_t h = 0; h < total_hops; ++h) {
         if (h == E.prehops) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
             t_acc = 0.0;
+            t_part = 0.0f;
             eoc = 0;
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k) occtime[k] = 0.0;
+            for (int k = 0; k < AS; ++k) occtime[k] = 0.0;
         }
-        // ---- publish fp32 energies to the warp's mirror
+        if (!inject && (h & 63) == 0) {
+            // 64 hops' worth of variates: lane l serves hops 2l and 2l+1 of this block
+            t_acc += (double)t_part;
+            t_part = 0.0f;
+            const uint64_t blk = (uint64_t)(h >> 6) * 32u + (uint64_t)lane;
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), key);
+            // unit exponential from (x+0.5)/2^32
+            const float e0 = -0.6931471805599453f * lg2_approx(fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+            const float e1 = -0.6931471805599453f * lg2_approx(fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+            __syncwarp();
+            reinterpret_cast<uint4 *>(rngbuf)[lane] = make_uint4(__float_as_uint(e0), r.y, __float_as_uint(e1), r.w);
+        }
+
+        // ---- publish scaled energies; per-lane source terms
+        float s_true[AS], src[AS], ea[AS], esig[AS];
+        const float *erow[AS];
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
-            eps32[k] = (float)eps64[k];
-            eps[lane + 32 * k] = eps32[k];
+        for (int k = 0; k < AS; ++k) {
+            const bool o = (occ[k] >> lane) & 1u;
+            s_true[k] = (float)eps64[k] * nb;
+            mir[lane + 32 * k] = s_true[k];
+            src[k] = o ? s_true[k] : BIGS;          // only occupied acceptors emit to acceptors
+            esig[k] = o ? 1.0f : -1.0f;             // occupied: i->e, t = s_e - s_i ; empty: e->i, t = s_i - s_e
+            ea[k] = o ? -s_true[k] : s_true[k];
+            erow[k] = reinterpret_cast<const float *>(tbl + N * PITCH + lane + 32 * k) + (o ? 0 : 1);
         }
         __syncwarp();
 
-        bool act[SLOTS];
+        // ---- sweep: every allowed pair exactly once
+        float rsA[AS], rsE[AS];
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k) act[k] = ((occ[k] | elm[k]) >> lane) & 1u;
-
-        // ---- sweep: row sums over allowed targets (empty acceptors, then electrodes)
-        float rs[SLOTS];
+        for (int k = 0; k < AS; ++k) rsA[k] = rsE[k] = 0.0f;
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k) rs[k] = 0.0f;
-#pragma unroll
-        for (int kw = 0; kw < SLOTS; ++kw) {
+        for (int kw = 0; kw < AS; ++kw) {
             uint32_t mm = ~occ[kw] & accm[kw];
             while (mm) {
                 const int j = kw * 32 + __ffs(mm) - 1;
                 mm &= mm - 1;
-                const float ej = eps[j];
-                const float2 *row = tbl + j * pitch2 + lane;
+                const float sj = mir[j];
+                const float2 *row = tbl + j * PITCH + lane;
 #pragma unroll
-                for (int k = 0; k < SLOTS; ++k) {
-                    const float r = ma_rate(row[32 * k], ej, eps32[k], negbeta);
-                    if (act[k]) rs[k] += r;
+                for (int k = 0; k < AS; ++k) {
+                    const float2 v = row[32 * k];
+                    const float t = fmaf(v.y, pb, sj - src[k]);
+                    rsA[k] = fmaf(v.x, ex2_approx(fminf(t, 0.0f)), rsA[k]);
                 }
             }
         }
-        for (int e = 0; e < P; ++e) {
-            const int j = N + e;
-            const float ej = eps[j];
-            const float2 *row = tbl + j * pitch2 + lane;
+        if (PT > 0) {
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k) {
-                if (32 * k < N) {  // slots holding only electrode rows have no electrode targets
-                    const float r = ma_rate(row[32 * k], ej, eps32[k], negbeta);
-                    if (act[k]) rs[k] += r;
+            for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
+#pragma unroll
+                for (int k = 0; k < AS; ++k) {
+                    const float t = fmaf(esig[k], se_reg[e], ea[k]);
+                    rsE[k] = fmaf(erow[k][e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rsE[k]);
+                }
+            }
+        } else {
+            for (int e = 0; e < P; ++e) {
+                const float se = mir[32 * AS + e];
+#pragma unroll
+                for (int k = 0; k < AS; ++k) {
+                    const float t = fmaf(esig[k], se, ea[k]);
+                    rsE[k] = fmaf(erow[k][e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rsE[k]);
                 }
             }
         }
 
-        // ---- first level: fp64 prefix over rows in row-major order
-        double pre[SLOTS];
+        // ---- first level: fp64 prefix over lanes (lane-major event order)
+        float rs[AS];
+        double pre[AS];
         double base = 0.0;
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
+        for (int k = 0; k < AS; ++k) {
+            rs[k] = rsA[k] + rsE[k];
             pre[k] = warp_incl_scan((double)rs[k], lane) + base;
             base = __shfl_sync(FULL, pre[k], 31);
         }
@@ -214,44 +239,33 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 
         // ---- random variates
         double r_pick;
-        float dt;
+        double dtd = 0.0;
         if (!inject) {
-            if ((h & 63) == 0) {
-                const uint64_t blk = (uint64_t)(h >> 6) * 32u + (uint64_t)lane;
-                rnd = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), key);
-            }
-            const int q = (int)(h & 63);
-            const uint32_t a = (q & 1) ? rnd.z : rnd.x;
-            const uint32_t b = (q & 1) ? rnd.w : rnd.y;
-            const uint32_t x1 = __shfl_sync(FULL, a, q >> 1);
-            const uint32_t x2 = __shfl_sync(FULL, b, q >> 1);
-            const float u1 = fmaf((float)x1, 2.3283064365386963e-10f, 1.1641532182693481e-10f);  // (x+0.5)/2^32
-            dt = (-0.6931471805599453f * lg2_approx(u1)) * rcp_approx((float)total);
+            const uint2 rv = rngbuf[h & 63];
+            const float dt = __uint_as_float(rv.x) * rcp_approx((float)total);
+            t_part += dt;
+            if (DBG) dtd = (double)dt;
             const double ts = total * 2.3283064365386963e-10;
-            r_pick = fma((double)x2, ts, 0.5 * ts);
-            t_acc += (double)dt;
+            r_pick = fma((double)rv.y, ts, 0.5 * ts);
         } else {
-            const double ek = E.stream_e[m * total_hops + h];
-            const float uk = E.stream_u[m * total_hops + h];
-            const double dt64 = ek / total;  // simulation.go:297
-            dt = (float)dt64;
-            r_pick = (double)uk * total;     // simulation.go:164
-            t_acc += dt64;
+            dtd = E.stream_e[m * total_hops + h] / total;          // simulation.go:297
+            r_pick = (double)E.stream_u[m * total_hops + h] * total;  // simulation.go:164
+            t_acc += dtd;
         }
 
-        // ---- pick the row
+        // ---- pick the lane
         int wslot = -1, wlane = 0;
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k) {
+        for (int k = 0; k < AS; ++k) {
             const uint32_t bal = __ballot_sync(FULL, pre[k] >= r_pick);
             if (wslot < 0 && bal) {
                 wslot = k;
                 wlane = __ffs(bal) - 1;
             }
         }
-        if (wslot < 0) {  // r_pick rounded above total: take the last row with a positive sum
+        if (wslot < 0) {  // r_pick rounded above total: last lane with a positive sum
 #pragma unroll
-            for (int k = SLOTS - 1; k >= 0; --k) {
+            for (int k = AS - 1; k >= 0; --k) {
                 const uint32_t bal = __ballot_sync(FULL, rs[k] > 0.0f);
                 if (wslot < 0 && bal) {
                     wslot = k;
@@ -259,62 +273,90 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
                 }
             }
         }
-        const int from = wslot * 32 + wlane;
-        double excl = 0.0;
+        const int istar = wslot * 32 + wlane;
+        float rf_mine = 0.0f, rsA_mine = 0.0f;
+        bool rowocc = false;
 #pragma unroll
-        for (int k = 0; k < SLOTS; ++k)
-            if (k == wslot) excl = pre[k] - (double)rs[k];
-        const double rres = r_pick - __shfl_sync(FULL, excl, wlane);
+        for (int k = 0; k < AS; ++k)
+            if (k == wslot) {
+                rf_mine = (float)(r_pick - (pre[k] - (double)rs[k]));
+                rsA_mine = rsA[k];
+                rowocc = (occ[k] >> wlane) & 1u;
+            }
+        const float rf = __shfl_sync(FULL, rf_mine, wlane);
+        const float s_star = mir[istar];
 
-        // ---- second level: re-evaluate row `from` lane-parallel over its targets
-        const float e_from = eps[from];
-        int to = -1;
-        double accum = 0.0;
-        uint32_t nzA[SLOTS], nzE = 0;
+        // ---- second level: re-evaluate the winning lane's targets lane-parallel
+        int from, to;
+        const float *ecol = reinterpret_cast<const float *>(tbl + (N + lane) * PITCH + istar);  // electrode `lane` vs istar
+        if (rowocc) {
+            from = istar;
+            to = -1;
+            const float rsA_star = __shfl_sync(FULL, rsA_mine, wlane);
+            const bool tryA = rf < rsA_star;
+            if (tryA) {  // acceptor targets: istar -> empty j
+                float thr = rf;
+                int lastpos = -1;
 #pragma unroll
-        for (int kw = 0; kw < SLOTS; ++kw) {
-            nzA[kw] = 0;
-            if (accm[kw]) {
-                const int j = lane + 32 * kw;
+                for (int kw = 0; kw < AS; ++kw) {
+                    if (to < 0 && (~occ[kw] & accm[kw])) {
+                        float rr = 0.0f;
+                        if (((~occ[kw] & accm[kw]) >> lane) & 1u) {
+                            const float2 v = tbl[(lane + 32 * kw) * PITCH + istar];
+                            rr = v.x * ex2_approx(fminf(fmaf(v.y, pb, s_true[kw] - s_star), 0.0f));
+                        }
+                        const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+                        if (nz) {
+                            lastpos = kw * 32 + 31 - __clz(nz);
+                            const float s = warp_incl_scan_f(rr, lane);
+                            const uint32_t bal = __ballot_sync(FULL, s >= thr) & nz;
+                            if (bal) to = kw * 32 + __ffs(bal) - 1;
+                            thr -= __shfl_sync(FULL, s, 31);
+                        }
+                    }
+                }
+                if (to < 0) to = lastpos;  // residual rounded past the group's end: its last positive target
+            }
+            if (to < 0) {  // electrode targets: istar -> e   (or acceptor group empty / exhausted)
                 float rr = 0.0f;
-                if (((~occ[kw] & accm[kw]) >> lane) & 1u) rr = ma_rate(tbl[j * pitch2 + from], eps32[kw], e_from, negbeta);
-                nzA[kw] = __ballot_sync(FULL, rr > 0.0f);
-                if (to < 0 && nzA[kw]) {
-                    const double s = warp_incl_scan((double)rr, lane) + accum;
-                    const uint32_t bal = __ballot_sync(FULL, s >= rres) & nzA[kw];
-                    if (bal) to = kw * 32 + __ffs(bal) - 1;
-                    accum = __shfl_sync(FULL, s, 31);
+                if (lane < P) rr = ecol[0] * ex2_approx(fminf(mir[32 * AS + lane] - s_star, 0.0f));
+                const int e = pick_in_group(rr, tryA ? BIGS : rf - rsA_star, lane);
+                if (e >= 0) to = N + e;
+            }
+            if (to < 0 && !tryA) {  // electrode group empty although rf >= rsA (rounding): last acceptor target
+#pragma unroll
+                for (int kw = AS - 1; kw >= 0; --kw) {
+                    if (to < 0 && (~occ[kw] & accm[kw])) {
+                        float rr = 0.0f;
+                        if (((~occ[kw] & accm[kw]) >> lane) & 1u) {
+                            const float2 v = tbl[(lane + 32 * kw) * PITCH + istar];
+                            rr = v.x * ex2_approx(fminf(fmaf(v.y, pb, s_true[kw] - s_star), 0.0f));
+                        }
+                        const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+                        if (nz) to = kw * 32 + 31 - __clz(nz);
+                    }
                 }
             }
-        }
-        if (from < N) {
+            if (to < 0) {
+                dead = true;
+                break;
+            }
+        } else {  // empty acceptor: events e -> istar
+            to = istar;
             float rr = 0.0f;
-            if (lane < P) rr = ma_rate(tbl[(N + lane) * pitch2 + from], eps[N + lane], e_from, negbeta);
-            nzE = __ballot_sync(FULL, rr > 0.0f);
-            if (to < 0 && nzE) {
-                const double s = warp_incl_scan((double)rr, lane) + accum;
-                const uint32_t bal = __ballot_sync(FULL, s >= rres) & nzE;
-                if (bal) to = N + __ffs(bal) - 1;
+            if (lane < P) rr = ecol[1] * ex2_approx(fminf(s_star - mir[32 * AS + lane], 0.0f));
+            const int e = pick_in_group(rr, rf, lane);
+            if (e < 0) {
+                dead = true;
+                break;
             }
-        }
-        if (to < 0) {  // residual rounded past the row's end: last target with a positive rate
-            if (nzE) to = N + 31 - __clz(nzE);
-            else {
-#pragma unroll
-                for (int kw = SLOTS - 1; kw >= 0; --kw)
-                    if (to < 0 && nzA[kw]) to = kw * 32 + 31 - __clz(nzA[kw]);
-            }
-        }
-        if (to < 0) {
-            dead = true;
-            break;
+            from = N + e;
         }
 
         // ---- tallies (simulation.go:309-317: pre-hop occupation, antisymmetric traffic)
-        if (RECORD && h >= E.prehops) {
-            const double dtd = inject ? (E.stream_e[m * total_hops + h] / total) : (double)dt;
+        if (DBG && h >= E.prehops) {
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k)
+            for (int k = 0; k < AS; ++k)
                 if ((occ[k] >> lane) & 1u) occtime[k] += dtd;
             if (lane == 0) {
                 if (E.traffic) {
@@ -333,70 +375,85 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
         // ---- apply the hop (simulation.go:107-130)
         if (from < N) {
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k) {
+            for (int k = 0; k < AS; ++k) {
                 if (k == (from >> 5)) occ[k] &= ~(1u << (from & 31));
-                eps64[k] -= (double)tbl[from * pitch2 + lane + 32 * k].y;
+                eps64[k] -= (double)tbl[from * PITCH + lane + 32 * k].y;
             }
         } else if (lane == from - N) eoc -= 1;
         if (to < N) {
 #pragma unroll
-            for (int k = 0; k < SLOTS; ++k) {
+            for (int k = 0; k < AS; ++k) {
                 if (k == (to >> 5)) occ[k] |= (1u << (to & 31));
-                eps64[k] += (double)tbl[to * pitch2 + lane + 32 * k].y;
+                eps64[k] += (double)tbl[to * PITCH + lane + 32 * k].y;
             }
         } else if (lane == to - N) eoc += 1;
     }
 
     // ---- results
+    t_acc += (double)t_part;
     if (dead) t_acc = __longlong_as_double(0x7ff0000000000000LL);  // +inf, as time_step = e/0 would give
     if (lane == 0) E.time[m] = t_acc;
     if (lane < P) E.electrode_occ[m * P + lane] = (int64_t)eoc;
 #pragma unroll
-    for (int k = 0; k < SLOTS; ++k) {
+    for (int k = 0; k < AS; ++k) {
         const int i = lane + 32 * k;
         if (i < N) {
             if (E.occupation_out) E.occupation_out[m * N + i] = (occ[k] >> lane) & 1u;
-            if (RECORD && E.avg_occupation) E.avg_occupation[m * N + i] = occtime[k];
+            if (DBG && E.avg_occupation) E.avg_occupation[m * N + i] = occtime[k];
+            if (E.site_energies_out) E.site_energies_out[m * S + i] = eps64[k];
         }
-        if (i < S && E.site_energies_out) E.site_energies_out[m * S + i] = eps64[k];
     }
+    if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)(float)E.electrode_v[m * P + lane];
 }
 
-// ---- parity probe: energies + dense rate matrix of one state with the fast kernel's arithmetic
+// ---- parity probe: energies + dense rate matrix of one state with the production arithmetic
 __global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, const double *electrode_v, float kT,
                                  const uint8_t *occ, float *se_io, int se_given, float *rates) {
-    const int N = L.N, P = L.P, S = L.S, pitch2 = L.pitch2;
+    const int N = L.N, S = L.S, pitch = L.pitchf;
     const int lane = threadIdx.x;
     if (!se_given) {
         for (int i = lane; i < S; i += 32) {
             double e = (i < N) ? (double)(float)E_constant[i] : (double)(float)electrode_v[i - N];
             if (i < N)
                 for (int j = 0; j < N; ++j)
-                    if (!occ[j]) e -= (double)L.tbl[j * pitch2 + i].y;
+                    if (!occ[j]) e -= (double)L.tblf[j * pitch + i].y;
             se_io[i] = (float)e;
         }
     }
     __syncwarp();
-    const float negbeta = -1.4426950408889634f / kT;
+    const float nb = -1.4426950408889634f / kT, pb = -nb;
     for (int idx = lane; idx < S * S; idx += 32) {
         const int i = idx / S, j = idx % S;
         bool ok = (i != j) && !(i >= N && j >= N);
         if (ok && i < N) ok = occ[i] != 0;
         if (ok && j < N) ok = occ[j] == 0;
-        rates[idx] = ok ? ma_rate(L.tbl[j * pitch2 + i], se_io[j], se_io[i], negbeta) : 0.0f;
+        float r = 0.0f;
+        if (ok) {
+            const float si = se_io[i] * nb, sj = se_io[j] * nb;
+            if (i < N && j < N) {
+                const float2 v = L.tblf[j * pitch + i];
+                r = v.x * ex2_approx(fminf(fmaf(v.y, pb, sj - si), 0.0f));
+            } else if (i < N) {  // i -> electrode j
+                r = L.tblf[j * pitch + i].x * ex2_approx(fminf(sj - si, 0.0f));
+            } else {             // electrode i -> acceptor j
+                r = L.tblf[i * pitch + j].y * ex2_approx(fminf(sj - si, 0.0f));
+            }
+        }
+        rates[idx] = r;
     }
 }
 
-template <int SLOTS>
+template <int AS, int PT>
 static cudaError_t launch_fast_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
-    const bool record = E.avg_occupation || E.traffic || E.trace;
+    const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e;
     // warps per CTA: large enough to amortise the table copy, small enough to balance small ensembles
     int warps = 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
     const int threads = warps * 32;
-    const size_t smem = (size_t)L.S * L.pitch2 * sizeof(float2) + (size_t)warps * 32 * SLOTS * sizeof(float);
+    const size_t smem = (size_t)L.S * (32 * AS + 1) * sizeof(float2) + (size_t)warps * (32 * AS + 32) * sizeof(float) +
+                        (size_t)warps * 64 * sizeof(uint2);
     const unsigned grid = (unsigned)((E.B + warps - 1) / warps);
-    auto kern = record ? kmc_fast_kernel<SLOTS, true> : kmc_fast_kernel<SLOTS, false>;
+    auto kern = dbg ? kmc_fast_kernel<AS, PT, true> : kmc_fast_kernel<AS, PT, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, threads, smem, st>>>(L, E);
@@ -406,11 +463,17 @@ static cudaError_t launch_fast_t(const LayoutDev &L, const EnsembleDev &E, cudaS
 
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
     if (E.B <= 0) return cudaSuccess;
-    switch (L.slots) {
-        case 1: return launch_fast_t<1>(L, E, st, launches);
-        case 2: return launch_fast_t<2>(L, E, st, launches);
-        default: return cudaErrorInvalidValue;
+    const int as = (L.N + 31) / 32;
+    if (as <= 1) {
+        if (L.P == 8) return launch_fast_t<1, 8>(L, E, st, launches);
+        if (L.P == 2) return launch_fast_t<1, 2>(L, E, st, launches);
+        return launch_fast_t<1, 0>(L, E, st, launches);
     }
+    if (as == 2) {
+        if (L.P == 8) return launch_fast_t<2, 8>(L, E, st, launches);
+        return launch_fast_t<2, 0>(L, E, st, launches);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,

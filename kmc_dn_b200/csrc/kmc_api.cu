@@ -123,7 +123,20 @@ extern "C" kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const
             if (i != j && i < N && j < N) v.y = IR / d32[(size_t)i * S + j];
             tbl[(size_t)j * D.pitch2 + i] = v;
         }
-    int rc = upload(&D.tbl, tbl) || upload(&D.d32, d32) || upload(&D.tc32, tc32) || upload(&D.d64, d64) ||
+    // production table: acceptor sources only
+    D.pitchf = 32 * ((N + 31) / 32) + 1;
+    if (N == 0) D.pitchf = 33;
+    std::vector<float2> tblf((size_t)S * D.pitchf, make_float2(0.f, 0.f));
+    for (int j = 0; j < S; ++j)
+        for (int i = 0; i < N; ++i) {
+            float2 v = make_float2(0.f, 0.f);
+            if (i != j && keep[(size_t)i * S + j]) v.x = D.nu32 * tc32[(size_t)i * S + j];
+            if (j < N) {
+                if (i != j) v.y = IR / d32[(size_t)i * S + j];
+            } else if (keep[(size_t)j * S + i]) v.y = D.nu32 * tc32[(size_t)j * S + i];
+            tblf[(size_t)j * D.pitchf + i] = v;
+        }
+    int rc = upload(&D.tblf, tblf) || upload(&D.tbl, tbl) || upload(&D.d32, d32) || upload(&D.tc32, tc32) || upload(&D.d64, d64) ||
              upload(&D.tc64, tc64) || upload(&D.pairs, pairs);
     if (rc) {
         delete lay;
@@ -135,7 +148,7 @@ extern "C" kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const
 extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     if (!lay) return;
     cudaSetDevice(lay->device);
-    cudaFree(lay->dev.tbl); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
+    cudaFree(lay->dev.tbl); cudaFree(lay->dev.tblf); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
     cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
     cudaFree(lay->ws);
     delete lay;
@@ -157,17 +170,20 @@ size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");
     if (a->B < 0 || a->hops < 0 || a->prehops < 0) return fail("kmcb200_run_ensemble: negative size");
-    if (a->mode < 0 || a->mode > 3) return fail("kmcb200_run_ensemble: unknown mode");
+    if (a->mode < 0 || a->mode > 4) return fail("kmcb200_run_ensemble: unknown mode");
     if (!a->E_constant && !(a->basis && a->electrode_v)) return fail("kmcb200_run_ensemble: need E_constant or basis+electrode_v");
     if (lay->dev.P > 0 && !a->electrode_v) return fail("kmcb200_run_ensemble: electrode_v is required");
     if (!a->kT || !a->time || !a->electrode_occ) return fail("kmcb200_run_ensemble: kT/time/electrode_occ are required");
     if (a->mode == KMCB200_MODE_PY && !a->stream_u64) return fail("kmcb200_run_ensemble: MODE_PY replays an injected stream (stream_u64)");
     if ((a->mode == KMCB200_MODE_GO_SIMULATE || a->mode == KMCB200_MODE_GO_RECORDPLUS) && !(a->stream_e && a->stream_u))
         return fail("kmcb200_run_ensemble: Go replay modes need stream_e and stream_u");
-    if (a->mode == KMCB200_MODE_FAST && ((a->stream_e != nullptr) != (a->stream_u != nullptr)))
+    const bool warp_kernel = a->mode == KMCB200_MODE_FAST || a->mode == KMCB200_MODE_FAST_REFORDER;
+    if (warp_kernel && ((a->stream_e != nullptr) != (a->stream_u != nullptr)))
         return fail("kmcb200_run_ensemble: stream_e and stream_u come together");
-    if (a->mode == KMCB200_MODE_FAST && lay->dev.S > 64)
-        return fail("kmcb200_run_ensemble: fast kernel supports N+P <= 64 in this build");
+    if (a->mode == KMCB200_MODE_FAST && lay->dev.N > 64)
+        return fail("kmcb200_run_ensemble: fast kernel supports N <= 64 acceptors in this build");
+    if (a->mode == KMCB200_MODE_FAST_REFORDER && lay->dev.S > 64)
+        return fail("kmcb200_run_ensemble: reference-order kernel supports N+P <= 64");
     if (lay->dev.P > 32) return fail("kmcb200_run_ensemble: more than 32 electrodes unsupported");
     return 0;
 }
@@ -182,7 +198,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     const int N = D.N, P = D.P, S = D.S;
     const int64_t B = a->B, H = a->prehops + a->hops;
     const bool dev_ptrs = a->flags & KMCB200_FLAG_DEVICE_PTRS;
-    const bool exact = a->mode != KMCB200_MODE_FAST;
+    const bool exact = a->mode != KMCB200_MODE_FAST && a->mode != KMCB200_MODE_FAST_REFORDER;
 
     EnsembleDev E{};
     E.B = B; E.hops = a->hops; E.prehops = a->prehops; E.mode = a->mode;
@@ -252,7 +268,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     }
 
     int launches = 0;
-    cudaError_t le = exact ? launch_exact(D, E, st, &launches) : launch_fast(D, E, st, &launches);
+    cudaError_t le = exact ? launch_exact(D, E, st, &launches)
+                           : (a->mode == KMCB200_MODE_FAST_REFORDER ? launch_reforder(D, E, st, &launches)
+                                                                    : launch_fast(D, E, st, &launches));
     g_launches += launches;
     if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));
 

@@ -14,6 +14,11 @@ struct LayoutDev {
     //                                   I_0*R/d[i][j] for acceptor-acceptor pairs i!=j, else 0 }
     // i.e. indexed [target j][source i]; fp32 narrowing as simulationWrapper.go:37-56.
     float2 *tbl;
+    // production table (hop_fast.cu): acceptor sources only, tblf[j*pitchf + i], pitchf = 32*ceil(N/32)+1:
+    //   target j <  N : { nu*tc[i][j], I_0*R/d[i][j] }      (i != j, else 0)
+    //   target j >= N : { nu*tc[i][j], nu*tc[j][i] }        (acceptor i <-> electrode j-N, both directions)
+    float2 *tblf;
+    int pitchf;
     // replay tables (row-major, exactly the caller's values)
     float *d32, *tc32;       // [S*S] narrowed (Go semantics)
     double *d64, *tc64;      // [S*S] (numba semantics)
@@ -37,6 +42,7 @@ struct EnsembleDev {
 
 // launchers (return cudaError_t of the launch)
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
+cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,
                          const uint8_t *occ, float *se_io, int se_given, float *rates_out, cudaStream_t st,

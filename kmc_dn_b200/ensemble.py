@@ -10,7 +10,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, FLAG_DEVICE_PTRS  # noqa: F401
+from ._lib import (MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER,  # noqa: F401
+                   FLAG_DEVICE_PTRS)
 
 
 def _host(a, dtype):

@@ -119,12 +119,12 @@ def test_replay_go_pruned_list(golden_py):
     lay.close()
 
 
-def test_fast_kernel_replays_oracle_until_a_rounding_tie(golden_py):
-    """The production kernel keeps the reference's row-major event order, so under an injected stream it
-    follows the fp32 Go restatement hop for hop; it may part only where u*total falls within rounding
-    distance of a list boundary (fp64 prefix + ex2.approx vs sequential fp32 sum + exp)."""
+def test_reference_order_kernel_replays_oracle_until_a_rounding_tie(golden_py):
+    """MODE_FAST_REFORDER = production arithmetic (fp32 rates via ex2.approx, fp64 energies / prefix / time) with
+    the reference's row-major event order, so under an injected stream it follows the fp32 Go restatement hop
+    for hop; it may part only where u*total falls within rounding distance of a list boundary."""
     from oracle import oracle
-    from kmc_dn_b200.ensemble import MODE_FAST
+    from kmc_dn_b200.ensemble import MODE_FAST_REFORDER as MODE_FAST
     agree = []
     for name, c in golden_py.items():
         hops = 4000
@@ -184,6 +184,37 @@ def test_fast_kernel_incremental_energies_do_not_drift(golden_py):
     lay.close()
 
 
+def test_fast_kernel_one_hop_event_distribution_matches_oracle_rates(golden_py, fixtures_subset):
+    """Order-independent check of the production pick: from one fixed state, 2^18 members take ONE hop each;
+    the empirical distribution over (from,to) must match rate_ij / sum(rate) of the oracle (chi-square), and
+    no disallowed pair may ever be chosen."""
+    from oracle import oracle
+    cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "c2_grid_N16_P8": golden_py["c2_grid_N16_P8"],
+             "n5_p3_hot": golden_py["n5_p3_hot"], "XOR_wide/test3": _fixture_case(fixtures_subset["XOR_wide/test3"])}
+    B = 1 << 18
+    for name, c in cases.items():
+        S = c["N"] + c["P"]
+        _, r_o = oracle.go_rates(c["N"], c["P"], c["nu"], c["kT"], c["I_0"], c["R"], c["occupation"], c["distances"],
+                                 c["E_constant"], c["transitions_constant"], site_energies_of(c))
+        p = r_o.astype(np.float64).ravel(); p /= p.sum()
+        lay = _layout(c)
+        r = lay.run(1, c["kT"], np.tile(c["electrode_v"], (B, 1)), E_constant=np.tile(c["E_constant"], (B, 1)),
+                    occupation0=c["occupation"], seed=77, trace=True)
+        lay.close()
+        ev = r["trace"][:, 0, 0].astype(np.int64) * S + r["trace"][:, 0, 1]
+        cnt = np.bincount(ev, minlength=S * S).astype(np.float64)
+        assert cnt[p == 0].sum() == 0, name  # structurally forbidden pairs are never picked
+        big = p * B >= 20
+        obs = np.append(cnt[big], cnt[~big].sum()); exp = np.append(p[big] * B, p[~big].sum() * B)
+        keep = exp > 0
+        chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+        dof = keep.sum() - 1
+        assert chi2 < dof + 5 * np.sqrt(2 * dof) + 5, (name, chi2, dof)
+        # the dwell times are Exp(total): mean of time over members = 1/total
+        total = r_o.astype(np.float64).sum()
+        assert r["time"].mean() * total == pytest.approx(1.0, abs=5 / np.sqrt(B))
+
+
 # ------------------------------------------------------------------ check 3: statistics
 def _five_run_D(f, cur):
     mu, sd = cur.mean(0), cur.std(0)
@@ -197,8 +228,8 @@ def test_fast_kernel_currents_pass_reference_acceptance(fixtures_subset):
     rel = []
     for name, f in fixtures_subset.items():
         c = _fixture_case(f)
-        hops = 5_000_000 if "5M" in name else 1_000_000
-        hops //= 4  # quarter-length runs: our sigma doubles, D's variance term absorbs it
+        hops = 5_000_000 if "5M" in name else 1_000_000  # same lengths as the fixtures (generate_tests.py:169-171);
+        # shorter runs would bias the small currents: the all-empty start injects ~N-M holes once
         lay = _layout(c)
         # fixtures were generated by wrapperSimulateRecordPlus => all-empty start (generate_tests.py:51)
         r = lay.run(hops, c["kT"], np.tile(c["electrode_v"], (5, 1)), E_constant=np.tile(c["E_constant"], (5, 1)),
@@ -339,7 +370,7 @@ def test_libsimulation_exports_through_goslices(fixtures_subset):
                 occupation=c["occupation"], distances=c["distances"], E_constant=c["E_constant"],
                 site_energies=site_energies_of(c), transitions_constant=c["transitions_constant"],
                 transitions=np.zeros((N + P, N + P)), problist=np.zeros((N + P) ** 2),
-                electrode_occupation=np.zeros(P, dtype=int), hops=250000)
+                electrode_occupation=np.zeros(P, dtype=int), hops=1000000)
     curs = []
     for _ in range(5):
         t, occ, eo = callGoSimulation(record=False, goSpecificFunction="wrapperSimulateRecordPlus", **base)
@@ -368,7 +399,7 @@ def test_libsimulation_exports_through_goslices(fixtures_subset):
         dns.append(dn)
     par = parrallelSimulation()
     for dn in dns:
-        par.addSimulation(dn, 250000)
+        par.addSimulation(dn, 1000000)
     par.runSimulation()
     for dn in dns:
         t, eo, cur = dn.parrallel_results[0]
