@@ -107,8 +107,10 @@ enum {
 };
 
 enum {
-    KMCB200_FLAG_DEVICE_PTRS = 1 /* every data pointer in the args is a device pointer on layout's GPU;
-                                    nothing is copied and the call returns after enqueueing on `stream` */
+    KMCB200_FLAG_DEVICE_PTRS = 1, /* every data pointer in the args is a device pointer on layout's GPU;
+                                     nothing is copied and the call returns after enqueueing on `stream` */
+    KMCB200_FLAG_NO_MEMO = 2      /* MODE_FAST: disable the per-warp state memoisation (results are
+                                     bit-identical either way; for testing and profiling)                */
 };
 
 typedef struct {
@@ -140,6 +142,8 @@ typedef struct {
     double *avg_occupation;     /* [B,N] or NULL: un-normalised occupied time (record)                 */
     double *traffic;            /* [B,S,S] or NULL (record)                                            */
     int32_t *trace;             /* [B,hops,2] or NULL: (from,to) of every recorded hop                 */
+    int64_t *misses;            /* [B] or NULL: hops whose rate structure had to be evaluated (MODE_FAST:
+                                   state-cache misses; equals prehops+hops with KMCB200_FLAG_NO_MEMO)     */
     void *stream;               /* cudaStream_t, NULL = default stream                                 */
 } kmcb200_ensemble_args;
 

@@ -13,6 +13,7 @@ SO_PATH = os.path.join(HERE, "libkmcb200.so")
 
 MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER = 0, 1, 2, 3, 4
 FLAG_DEVICE_PTRS = 1
+FLAG_NO_MEMO = 2
 
 
 class GoSlice(C.Structure):
@@ -29,7 +30,7 @@ class EnsembleArgs(C.Structure):
         ("stream_e", C.c_void_p), ("stream_u", C.c_void_p), ("stream_u64", C.c_void_p),
         ("time", C.c_void_p), ("electrode_occ", C.c_void_p), ("occupation_out", C.c_void_p),
         ("site_energies_out", C.c_void_p), ("avg_occupation", C.c_void_p), ("traffic", C.c_void_p),
-        ("trace", C.c_void_p), ("stream", C.c_void_p),
+        ("trace", C.c_void_p), ("misses", C.c_void_p), ("stream", C.c_void_p),
     ]
 
 

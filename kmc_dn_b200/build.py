@@ -18,6 +18,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 # per-file extra flags: the replay kernels must not contract a*b+c (Go on amd64 and numba never do)
 UNITS = {
     "hop_fast.cu": [],
+    "hop_memo.cu": [],
     "hop_reforder.cu": [],
     "hop_exact.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "kmc_api.cu": [],

@@ -223,6 +223,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         if (a->avg_occupation) need += a256(sizeof(double) * B * N);
         if (a->traffic) need += a256(sizeof(double) * (size_t)B * S * S);
         if (a->trace) need += a256(sizeof(int32_t) * (size_t)B * a->hops * 2);
+        if (a->misses) need += a256(sizeof(int64_t) * B);
     }
     if (need > lay->ws_bytes) {
         if (lay->ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ws)); lay->ws = nullptr; lay->ws_bytes = 0; }
@@ -238,6 +239,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         E.time = a->time; E.electrode_occ = a->electrode_occ; E.occupation_out = a->occupation_out;
         E.site_energies_out = a->site_energies_out; E.avg_occupation = a->avg_occupation; E.traffic = a->traffic;
         E.trace = a->trace;
+        E.misses = (long long *)a->misses;
         if (E.traffic) CU(cudaMemsetAsync(E.traffic, 0, sizeof(double) * (size_t)B * S * S, st));
     } else {
 #define H2D(field, T, count)                                                                          \
@@ -265,12 +267,19 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             CU(cudaMemsetAsync(E.traffic, 0, sizeof(double) * (size_t)B * S * S, st));
         }
         if (a->trace) E.trace = cv.take<int32_t>((size_t)B * a->hops * 2);
+        if (a->misses) E.misses = cv.take<long long>(B);
     }
 
     int launches = 0;
-    cudaError_t le = exact ? launch_exact(D, E, st, &launches)
-                           : (a->mode == KMCB200_MODE_FAST_REFORDER ? launch_reforder(D, E, st, &launches)
-                                                                    : launch_fast(D, E, st, &launches));
+    cudaError_t le;
+    if (exact) le = launch_exact(D, E, st, &launches);
+    else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
+    else if (D.N <= 32 && !getenv("KMCB200_NO_MEMO_KERNEL")) {
+        int logk = 4;
+        if (const char *ev = getenv("KMCB200_MEMO_LOGK")) logk = atoi(ev);
+        if (a->flags & KMCB200_FLAG_NO_MEMO) logk = -1;
+        le = launch_memo(D, E, logk, st, &launches);
+    } else le = launch_fast(D, E, st, &launches);
     g_launches += launches;
     if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));
 
@@ -284,6 +293,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         D2H(avg_occupation, double, (size_t)B * N)
         D2H(traffic, double, (size_t)B * S * S)
         D2H(trace, int32_t, (size_t)B * a->hops * 2)
+        D2H(misses, int64_t, (size_t)B)
 #undef D2H
         CU(cudaStreamSynchronize(st));
     }

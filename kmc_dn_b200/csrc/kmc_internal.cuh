@@ -37,11 +37,13 @@ struct EnsembleDev {
     const double *stream_e; const float *stream_u; const double *stream_u64;
     double *time; int64_t *electrode_occ; uint8_t *occupation_out; double *site_energies_out;
     double *avg_occupation; double *traffic; int32_t *trace;
+    long long *misses;  // [B] rate-structure evaluations (cache misses) per member, or null
     double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
 };
 
 // launchers (return cudaError_t of the launch)
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
+cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches);
 cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,

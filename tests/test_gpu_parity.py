@@ -165,8 +165,12 @@ def test_fast_kernel_energies_and_rates_vs_oracle(golden_py, fixtures_subset):
             np.testing.assert_allclose(se_d, se_o, rtol=1e-6, atol=1e-6 * scale, err_msg=name)
             _, r_same = lay.probe_rates(c["E_constant"], c["electrode_v"], c["kT"], occ, site_energies=se_o)
             assert ((r_same > 0) == (r_o > 0)).all() or np.abs(r_o[(r_same > 0) != (r_o > 0)]).max() < 1e-37
-            live = r_o > 1e-30
+            # entries below 2^-24 of the list total cannot move the Go loop's float32 cumulative list at all;
+            # they are checked to 2e-5 (|dE|/kT ~ 60 there: a float32 product dE*(1/kT) alone carries 4e-6)
+            live = r_o > 2.0 ** -24 * r_o.sum()
             np.testing.assert_allclose(r_same[live], r_o[live], rtol=1e-6, err_msg=name)
+            live = r_o > 1e-30
+            np.testing.assert_allclose(r_same[live], r_o[live], rtol=2e-5, err_msg=name)
             live = r_o > 1e-9 * r_o.max()
             np.testing.assert_allclose(r_d[live], r_o[live], rtol=1e-4 * max(1.0, 1.0 / c["kT"]), err_msg=name)
         lay.close()
@@ -283,6 +287,32 @@ def test_fast_kernel_results_do_not_depend_on_batching(golden_py):
     np.testing.assert_array_equal(a["time"], np.concatenate([b1["time"], b2["time"]]))
     np.testing.assert_array_equal(a["electrode_occupation"], np.concatenate([b1["electrode_occupation"], b2["electrode_occupation"]]))
     lay.close()
+
+
+def test_state_memoisation_is_transparent(golden_py, fixtures_subset):
+    """The per-warp state cache memoises a pure function of the occupation: with it disabled
+    (KMCB200_FLAG_NO_MEMO) every trajectory is bit-identical -- hop sequence, time, tallies, occupation --
+    and the cache really is used (rate structures evaluated on a small fraction of the hops)."""
+    cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
+             "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"], "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"])}
+    for name, c in cases.items():
+        B, hops = 24, 6000
+        V = np.tile(c["electrode_v"], (B, 1)) + np.linspace(0, 5, B)[:, None]
+        E = np.tile(c["E_constant"], (B, 1))
+        lay = _layout(c)
+        kw = dict(E_constant=E, occupation0=c["occupation"], prehops=500, seed=21, trace=True, want_occupation=True,
+                  want_site_energies=True, want_misses=True, record=True)
+        a = lay.run(hops, c["kT"], V, memo=True, **kw)
+        b = lay.run(hops, c["kT"], V, memo=False, **kw)
+        lay.close()
+        np.testing.assert_array_equal(a["trace"], b["trace"])
+        np.testing.assert_array_equal(a["time"], b["time"])
+        np.testing.assert_array_equal(a["electrode_occupation"], b["electrode_occupation"])
+        np.testing.assert_array_equal(a["occupation"], b["occupation"])
+        np.testing.assert_array_equal(a["site_energies"], b["site_energies"])
+        np.testing.assert_array_equal(a["avg_occupation"], b["avg_occupation"])
+        assert (b["misses"] == hops + 500).all(), name
+        assert (a["misses"] < b["misses"]).all() and a["misses"].mean() < 0.6 * (hops + 500), (name, a["misses"].mean())
 
 
 def test_superposition_matvec_equals_explicit_E_constant(fixtures_subset):
