@@ -20,9 +20,8 @@
 //     The event order of the cumulative list is therefore lane-major instead of the reference's row-major
 //     (electrode->acceptor events sit in the acceptor's lane).  Any fixed order samples the same Markov
 //     chain; the row-major variant is kept in hop_reforder.cu for lock-step replay against the oracle.
-//   * energies are carried pre-scaled, s = eps * (-log2e/kT), so a rate is
-//         tc * exp2(min(0, s_to - s_from + kd*log2e/kT))   =  FADD, FFMA, FMNMX, MUFU.EX2, FFMA.
-//     Rows that may not act as a source carry s_from = +1e30 instead of a predicate.
+//   * a rate is tc * exp2(min(0, ((e_to - e_from) - kd) * (-log2e/kT))), in the reference's operation order
+//     (simulation.go:66-77).  Rows that may not act as a source carry e_from = -1e30 instead of a predicate.
 //   * table in shared memory, [target][source] float2: {nu*tc(i->j), I0*R/d_ij} for acceptor targets,
 //     {nu*tc(i->e), nu*tc(e->i)} for electrode targets; pitch 32*AS+1 float2 (conflict-free row- and
 //     column-wise).  fp32 narrowing as the cgo wrappers do (simulationWrapper.go:37-56).
@@ -91,10 +90,9 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 
     // ---- member parameters
     const float kT = (float)E.kT[m];
-    const float nb = -1.4426950408889634f / kT;  // energies are carried as s = eps*nb
-    const float pb = -nb;
+    const float nb = -1.4426950408889634f / kT;
     float se_reg[PT > 0 ? PT : 1];
-    if (lane < P) mir[32 * AS + lane] = (float)E.electrode_v[m * P + lane] * nb;
+    if (lane < P) mir[32 * AS + lane] = (float)E.electrode_v[m * P + lane];
     __syncwarp();
     if (PT > 0) {
 #pragma unroll
@@ -166,17 +164,16 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
         }
 
         // ---- publish scaled energies; per-lane source terms
-        float s_true[AS], src[AS], ea[AS], esig[AS];
+        float s_true[AS], src[AS], nbs[AS];
         const float *erow[AS];
         __syncwarp();
 #pragma unroll
         for (int k = 0; k < AS; ++k) {
             const bool o = (occ[k] >> lane) & 1u;
-            s_true[k] = (float)eps64[k] * nb;
+            s_true[k] = (float)eps64[k];
             mir[lane + 32 * k] = s_true[k];
-            src[k] = o ? s_true[k] : BIGS;          // only occupied acceptors emit to acceptors
-            esig[k] = o ? 1.0f : -1.0f;             // occupied: i->e, t = s_e - s_i ; empty: e->i, t = s_i - s_e
-            ea[k] = o ? -s_true[k] : s_true[k];
+            src[k] = o ? s_true[k] : -BIGS;         // only occupied acceptors emit to acceptors
+            nbs[k] = o ? nb : -nb;                  // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
             erow[k] = reinterpret_cast<const float *>(tbl + N * PITCH + lane + 32 * k) + (o ? 0 : 1);
         }
         __syncwarp();
@@ -196,8 +193,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 #pragma unroll
                 for (int k = 0; k < AS; ++k) {
                     const float2 v = row[32 * k];
-                    const float t = fmaf(v.y, pb, sj - src[k]);
-                    rsA[k] = fmaf(v.x, ex2_approx(fminf(t, 0.0f)), rsA[k]);
+                    rsA[k] += ma_rate(v, sj, src[k], nb);
                 }
             }
         }
@@ -206,7 +202,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
             for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
 #pragma unroll
                 for (int k = 0; k < AS; ++k) {
-                    const float t = fmaf(esig[k], se_reg[e], ea[k]);
+                    const float t = (se_reg[e] - s_true[k]) * nbs[k];
                     rsE[k] = fmaf(erow[k][e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rsE[k]);
                 }
             }
@@ -215,7 +211,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
                 const float se = mir[32 * AS + e];
 #pragma unroll
                 for (int k = 0; k < AS; ++k) {
-                    const float t = fmaf(esig[k], se, ea[k]);
+                    const float t = (se - s_true[k]) * nbs[k];
                     rsE[k] = fmaf(erow[k][e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rsE[k]);
                 }
             }
@@ -303,7 +299,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
                         float rr = 0.0f;
                         if (((~occ[kw] & accm[kw]) >> lane) & 1u) {
                             const float2 v = tbl[(lane + 32 * kw) * PITCH + istar];
-                            rr = v.x * ex2_approx(fminf(fmaf(v.y, pb, s_true[kw] - s_star), 0.0f));
+                            rr = ma_rate(v, s_true[kw], s_star, nb);
                         }
                         const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
                         if (nz) {
@@ -319,7 +315,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
             }
             if (to < 0) {  // electrode targets: istar -> e   (or acceptor group empty / exhausted)
                 float rr = 0.0f;
-                if (lane < P) rr = ecol[0] * ex2_approx(fminf(mir[32 * AS + lane] - s_star, 0.0f));
+                if (lane < P) rr = ecol[0] * ex2_approx(fminf((mir[32 * AS + lane] - s_star) * nb, 0.0f));
                 const int e = pick_in_group(rr, tryA ? BIGS : rf - rsA_star, lane);
                 if (e >= 0) to = N + e;
             }
@@ -330,7 +326,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
                         float rr = 0.0f;
                         if (((~occ[kw] & accm[kw]) >> lane) & 1u) {
                             const float2 v = tbl[(lane + 32 * kw) * PITCH + istar];
-                            rr = v.x * ex2_approx(fminf(fmaf(v.y, pb, s_true[kw] - s_star), 0.0f));
+                            rr = ma_rate(v, s_true[kw], s_star, nb);
                         }
                         const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
                         if (nz) to = kw * 32 + 31 - __clz(nz);
@@ -344,7 +340,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
         } else {  // empty acceptor: events e -> istar
             to = istar;
             float rr = 0.0f;
-            if (lane < P) rr = ecol[1] * ex2_approx(fminf(s_star - mir[32 * AS + lane], 0.0f));
+            if (lane < P) rr = ecol[1] * ex2_approx(fminf((s_star - mir[32 * AS + lane]) * nb, 0.0f));
             const int e = pick_in_group(rr, rf, lane);
             if (e < 0) {
                 dead = true;
@@ -406,43 +402,6 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
     if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)(float)E.electrode_v[m * P + lane];
 }
 
-// ---- parity probe: energies + dense rate matrix of one state with the production arithmetic
-__global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, const double *electrode_v, float kT,
-                                 const uint8_t *occ, float *se_io, int se_given, float *rates) {
-    const int N = L.N, S = L.S, pitch = L.pitchf;
-    const int lane = threadIdx.x;
-    if (!se_given) {
-        for (int i = lane; i < S; i += 32) {
-            double e = (i < N) ? (double)(float)E_constant[i] : (double)(float)electrode_v[i - N];
-            if (i < N)
-                for (int j = 0; j < N; ++j)
-                    if (!occ[j]) e -= (double)L.tblf[j * pitch + i].y;
-            se_io[i] = (float)e;
-        }
-    }
-    __syncwarp();
-    const float nb = -1.4426950408889634f / kT, pb = -nb;
-    for (int idx = lane; idx < S * S; idx += 32) {
-        const int i = idx / S, j = idx % S;
-        bool ok = (i != j) && !(i >= N && j >= N);
-        if (ok && i < N) ok = occ[i] != 0;
-        if (ok && j < N) ok = occ[j] == 0;
-        float r = 0.0f;
-        if (ok) {
-            const float si = se_io[i] * nb, sj = se_io[j] * nb;
-            if (i < N && j < N) {
-                const float2 v = L.tblf[j * pitch + i];
-                r = v.x * ex2_approx(fminf(fmaf(v.y, pb, sj - si), 0.0f));
-            } else if (i < N) {  // i -> electrode j
-                r = L.tblf[j * pitch + i].x * ex2_approx(fminf(sj - si, 0.0f));
-            } else {             // electrode i -> acceptor j
-                r = L.tblf[i * pitch + j].y * ex2_approx(fminf(sj - si, 0.0f));
-            }
-        }
-        rates[idx] = r;
-    }
-}
-
 template <int AS, int PT>
 static cudaError_t launch_fast_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e;
@@ -474,13 +433,6 @@ cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t s
         return launch_fast_t<2, 0>(L, E, st, launches);
     }
     return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,
-                         const uint8_t *occ, float *se_io, int se_given, float *rates, cudaStream_t st, int *launches) {
-    kmc_probe_kernel<<<1, 32, 0, st>>>(L, E_constant, electrode_v, (float)kT, occ, se_io, se_given, rates);
-    if (launches) ++*launches;
-    return cudaGetLastError();
 }
 
 }  // namespace kmcb200

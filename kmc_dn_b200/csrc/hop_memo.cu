@@ -1,31 +1,81 @@
 // hop_memo.cu -- production KMC hop loop with STATE MEMOISATION (KMCB200_MODE_FAST, N <= 32 acceptors).
 //
-// Same physics, arithmetic and event order as hop_fast.cu (read its header first).  What is added is the
-// GPU-native counterpart of the reference's state cache (goSimulation/simulation.go:222-223, 251-296,
-// 351-412): a trajectory revisits a few dozen occupation states over and over (C3: 16 states cover 80-99 %
-// of 1e5 hops), and in this kernel -- exactly as in simulateRecordPlus, which recomputes the energies from
-// scratch on a miss (simulation.go:378-386) -- the cumulative rate structure is a PURE function of the
-// occupation bit-mask, because the fp64 incremental energies are exact.  So every warp keeps a small
-// direct-mapped cache in shared memory:
+// Reference semantics being accelerated (MUTUEL/kmc_dn, paths relative to the reference tree):
+//   site energies      goSimulation/simulation.go:226-234  (E_const - I0*R*sum_{j empty} 1/d_ij)
+//   incremental update goSimulation/simulation.go:107-130  (makeJump)
+//   allowed pairs      goSimulation/simulation.go:40-55
+//   Miller-Abrahams    goSimulation/simulation.go:58-80
+//   cumulative list    goSimulation/simulation.go:267-276
+//   dwell time / pick  goSimulation/simulation.go:297-299, 163-188
+//   tallies            goSimulation/simulation.go:306-319
+//   state cache        goSimulation/simulation.go:222-223, 251-296, 351-412
+//
+// One warp = one trajectory; lane l owns acceptor l.  Physics, arithmetic and event order are those of
+// hop_fast.cu (read its header first): every allowed pair is evaluated exactly once per sweep -- lane i
+// evaluates i->j for the empty sites j (warp-uniform bit-loop) and, per electrode e, i->e if it is occupied or
+// e->i if it is empty; fp32 rates with MUFU.EX2, fp64 incremental energies (exact, drift-free), fp64 prefix
+// over the lane sums, two-level pick, Philox4x32-10 variates pooled in shared memory once per 64 hops.
+//
+// What this kernel adds is the GPU-native counterpart of the reference's state cache.  A trajectory revisits
+// a few dozen occupation states over and over (C3: 16 states cover 80-99 % of 1e5 hops), and here -- exactly as
+// in simulateRecordPlus, which recomputes the energies from scratch on a miss (simulation.go:378-386) -- the
+// cumulative rate structure is a PURE function of the occupation bit-mask, because the fp64 incremental
+// energies are exact.  Every warp keeps a direct-mapped cache in shared memory:
 //
 //     key   = 32-bit occupation mask              (slot = multiplicative hash, 2^LOGK slots)
 //     value = the fp64 inclusive prefix over the 32 lane sums (256 B: one double per lane, lane-private column)
 //
-// Hit:  the whole sweep (every allowed pair) and the fp64 scan are skipped; the hop costs one lookup, the
-//       first-level ballot, the second-level re-evaluation of ONE lane's targets, and the state update.
-// Miss: sweep + scan as in hop_fast.cu, then the prefix is parked in the slot.
+// Hit:  the sweep and the fp64 scan are skipped; the hop costs the lookup, the first-level ballot, the
+//       second-level re-evaluation of ONE lane's targets and the state update.
+// Miss: sweep + scan, then the prefix is parked in the slot.
 // Memoising a pure function cannot change a result: with the cache disabled (LOGK = -1 instantiation,
 // KMCB200_FLAG_NO_MEMO) the kernel produces bit-identical trajectories (tests/test_gpu_parity.py).
+// The reference's cache stores the full per-pair list per state (up to 150e6 floats per trajectory); here the
+// second level is recomputed instead of stored, so 256 B per state keeps 16 states per warp on chip.
 //
-// The reference's cache stores the full per-pair list per state (len(transitions) floats, up to 150e6 floats
-// per trajectory).  Here the second level is recomputed instead of stored: 256 B per state keeps 16 states
-// per warp on chip for 32 resident warps per SM.
+// Shared-memory accesses in the hop loop go through explicit ld/st.shared on 32-bit shared addresses: every
+// branch condition is then provably warp-uniform for the compiler (votes), and no generic-address arithmetic
+// is left in the loop.
 #include "kmc_device.cuh"
 #include "kmc_internal.cuh"
 
 namespace kmcb200 {
 
-#define BIGS 1.0e30f
+#define BIGE 1.0e30f
+#define ROWB 264u  // bytes per acceptor-target row of the pair table: 33 float2
+#define ELB 132u   // bytes per electrode row of the electrode planes: 33 float
+
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_d(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v)); }
+__device__ __forceinline__ void sts_u(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts_d(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void sts_u4(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
 
 // Kogge-Stone steps with the add predicated on the shuffle's in-range flag (SHFL + @p ADD, no select).
 __device__ __forceinline__ float scan_step_f(float v, int d) {
@@ -61,6 +111,13 @@ __device__ __forceinline__ double scan_d(double v) {
     return v;
 }
 
+// Miller-Abrahams factor in the reference's operation order (simulation.go:66-77): dE = e_to - e_from - kd,
+// rate = tc * exp(-dE/kT) for dE > 0, else tc.   nb = -log2(e)/kT.
+__device__ __forceinline__ float ma(float tc, float kd, float e_to, float e_from, float nb) {
+    const float dE = (e_to - e_from) - kd;
+    return tc * ex2_approx(fminf(dE * nb, 0.0f));
+}
+
 // first lane whose inclusive prefix reaches thr among lanes with a positive rate; if rounding put thr past the
 // end, the last positive lane; -1 if the group is empty.  STEPS = log2(lanes that can be positive).
 template <int STEPS>
@@ -72,44 +129,63 @@ __device__ __forceinline__ int pick_group(float rr, float thr) {
     return bal ? (__ffs(bal) - 1) : (31 - __clz(nz));
 }
 
+template <int LOGK>
+struct MemoGeom {
+    static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
+    static constexpr int KEYB = K > 4 ? K * 4 : 16;
+    static constexpr int WARP_BYTES = 256 + 512 + KEYB + K * 256;  // mirror | variates | keys | prefixes
+};
+
 template <int PT, int LOGK, bool DBG>
 __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
-    constexpr int PITCH = 33;
-    constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
+    using G = MemoGeom<LOGK>;
+    constexpr int K = G::K;
     constexpr int ESTEPS = (PT > 0 && PT <= 2) ? 1 : (PT > 0 && PT <= 4) ? 2 : (PT > 0 && PT <= 8) ? 3 : 5;
-    // per-warp shared memory (bytes): mirror 64 f32 | rng 64 x uint2 | keys K u32 (>=16 B) | cache K x 32 f64
-    constexpr int WARP_BYTES = 256 + 512 + (K > 4 ? K * 4 : 16) + K * 256;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *tbl = reinterpret_cast<float2 *>(smem_raw);
     const int N = L.N, S = L.S;
     const int P = PT > 0 ? PT : L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
-    for (int idx = tid; idx < S * PITCH; idx += blockDim.x) tbl[idx] = L.tblf[idx];
+    // ---- stage the layout: pair table for acceptor targets, two planes (i->e, e->i) for the electrodes
+    {
+        float2 *acc = reinterpret_cast<float2 *>(smem_raw);
+        float *elF = reinterpret_cast<float *>(smem_raw + (size_t)N * ROWB);
+        float *elR = elF + P * 33;
+        for (int idx = tid; idx < N * 33; idx += blockDim.x) acc[idx] = L.tblf[idx];
+        for (int idx = tid; idx < P * 33; idx += blockDim.x) {
+            const float2 v = L.tblf[N * 33 + idx];
+            elF[idx] = v.x;
+            elR[idx] = v.y;
+        }
+    }
     __syncthreads();
 
     const int64_t m = (int64_t)blockIdx.x * nwarps + warp;
     if (m >= E.B) return;
-    unsigned char *wbase = smem_raw + (((size_t)S * PITCH * sizeof(float2) + 15) & ~size_t(15)) + (size_t)warp * WARP_BYTES;
-    float *mir = reinterpret_cast<float *>(wbase);               // [0,32) acceptors, [32,64) electrodes
-    uint2 *rngbuf = reinterpret_cast<uint2 *>(wbase + 256);
-    uint32_t *keys = reinterpret_cast<uint32_t *>(wbase + 768);
-    double *cache = reinterpret_cast<double *>(wbase + 768 + (K > 4 ? K * 4 : 16));
 
+    const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
+    const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
+    const uint32_t a_mir = wb, a_rng = wb + 256, a_keys = wb + 768, a_cache = wb + 768 + G::KEYB;
+    const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
+    const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
+    const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
+    const uint32_t a_elR_e = a_elR + lane * ELB;      // + istar*4    : electrode lane -> istar
     const uint32_t accm = (N >= 32) ? ~0u : ((1u << N) - 1u);
 
     // ---- member parameters
-    const float kT = (float)E.kT[m];
-    const float nb = -1.4426950408889634f / kT;  // energies are carried as s = eps*nb
-    const float pb = -nb;
-    if (lane < P) mir[32 + lane] = (float)E.electrode_v[m * P + lane] * nb;
+    const float nb = -1.4426950408889634f / (float)E.kT[m];
+    const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;  // electrode `lane`
+    sts_f(a_mir + 128 + lane * 4, ve_mine);
     __syncwarp();
-    float se_reg[PT > 0 ? PT : 1];
+    float ve_reg[PT > 0 ? PT : 1];
     if (PT > 0) {
 #pragma unroll
-        for (int e = 0; e < (PT > 0 ? PT : 1); ++e) se_reg[e] = mir[32 + e];
+        for (int e = 0; e < (PT > 0 ? PT : 1); ++e) ve_reg[e] = lds_f(a_mir + 128 + e * 4);
     }
-    const float se_mine = (lane < P) ? mir[32 + lane] : 0.0f;  // electrode `lane` (second level)
+    if (K > 0) {  // empty cache: a key that hashes to another slot can never hit
+        if (lane < K) sts_u(a_keys + lane * 4, lane == 0 ? 1u : 0u);
+    }
 
     // ---- initial state
     bool o0 = false;
@@ -129,98 +205,86 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
         while (mm) {
             const int j = __ffs(mm) - 1;
             mm &= mm - 1;
-            eps64 -= (double)tbl[j * PITCH + lane].y;
+            eps64 -= (double)lds_f2(a_row_me + j * ROWB).y;
         }
     }
 
     const uint64_t gm = E.member_index0 + (uint64_t)m;
     const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
     const bool inject = DBG && E.stream_e != nullptr;
-    const int64_t total_hops = E.prehops + E.hops;
-    // byte offsets of this lane's table entries
-    const float2 *col_acc = tbl + lane * PITCH;        // + istar : pair (source istar -> target acceptor `lane`)
-    const float2 *col_el = tbl + (N + lane) * PITCH;   // + istar : pair (acceptor istar <-> electrode `lane`)
-    const float2 *row_me = tbl + lane;                 // + j*PITCH : pair (source `lane` -> target j)
+    const int64_t total_hops = E.prehops + E.hops, prehops = E.prehops;
 
     double t_acc = 0.0;
     float t_part = 0.0f;
     int eoc = 0;
     double occtime = 0.0;
-    uint32_t valid = 0;
     bool dead = false;
     long long n_miss = 0;
 
-    for (int64_t h0 = 0; h0 < total_hops && !dead; h0 += 64) {
-        const int nq = (total_hops - h0 < 64) ? (int)(total_hops - h0) : 64;
-        const int qreset = (E.prehops >= h0 && E.prehops < h0 + 64) ? (int)(E.prehops - h0) : -1;
+    int64_t h = 0;
+    while (h < total_hops && !dead) {
+        // a chunk never straddles a 64-hop variate block or the prehops boundary
+        const int q0 = (int)(h & 63);
+        int64_t hend = h - q0 + 64;
+        if (hend > total_hops) hend = total_hops;
+        if (h < prehops && hend > prehops) hend = prehops;
+        const int q1 = q0 + (int)(hend - h);
         if (!inject) {
             // 64 hops' worth of variates: lane l serves hops 2l and 2l+1 of this block
             t_acc += (double)t_part;
             t_part = 0.0f;
-            const uint64_t blk = (uint64_t)(h0 >> 6) * 32u + (uint64_t)lane;
+            const uint64_t blk = (uint64_t)(h >> 6) * 32u + (uint64_t)lane;
             const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), key);
             const float e0 = -0.6931471805599453f * lg2_approx(fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
             const float e1 = -0.6931471805599453f * lg2_approx(fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
             __syncwarp();
-            reinterpret_cast<uint4 *>(rngbuf)[lane] = make_uint4(__float_as_uint(e0), r.y, __float_as_uint(e1), r.w);
+            sts_u4(a_rng + lane * 16, make_uint4(__float_as_uint(e0), r.y, __float_as_uint(e1), r.w));
         }
-        for (int q = 0; q < nq; ++q) {
-            if (q == qreset) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
-                t_acc = 0.0;
-                t_part = 0.0f;
-                eoc = 0;
-                occtime = 0.0;
-            }
-            // ---- publish scaled energies
-            const float s_me = (float)eps64 * nb;
+        for (int q = q0; q < q1; ++q) {
+            // ---- publish the fp32 energies
+            const float e_me = (float)eps64;
             __syncwarp();
-            mir[lane] = s_me;
+            sts_f(a_mir + lane * 4, e_me);
             __syncwarp();
 
             // ---- cumulative structure of this state: cached or computed
             double pre;
             const uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-            const bool hit = (K > 0) && ((valid >> slot) & 1u) && (keys[slot] == occ);
+            bool hit = false;
+            if (K > 0) hit = __all_sync(FULL, lds_u(a_keys + slot * 4) == occ);
             if (hit) {
-                pre = cache[slot * 32 + lane];
+                pre = lds_d(a_cache + slot * 256 + lane * 8);
             } else {
                 if (DBG) ++n_miss;
                 const bool o = (occ >> lane) & 1u;
-                const float src = o ? s_me : BIGS;       // only occupied acceptors emit to acceptors
-                const float esig = o ? 1.0f : -1.0f;     // occupied: i->e, t = s_e - s_i ; empty: e->i, t = s_i - s_e
-                const float ea = o ? -s_me : s_me;
-                const float *erow = reinterpret_cast<const float *>(tbl + N * PITCH + lane) + (o ? 0 : 1);
+                const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
+                const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
+                const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
                 float rs = 0.0f;
                 uint32_t mm = ~occ & accm;
                 while (mm) {
                     const int j = __ffs(mm) - 1;
                     mm &= mm - 1;
-                    const float sj = mir[j];
-                    const float2 v = row_me[j * PITCH];
-                    const float t = fmaf(v.y, pb, sj - src);
-                    rs = fmaf(v.x, ex2_approx(fminf(t, 0.0f)), rs);
+                    const float ej = lds_f(a_mir + j * 4);
+                    const float2 v = lds_f2(a_row_me + j * ROWB);
+                    rs += ma(v.x, v.y, ej, src, nb);
                 }
                 if (PT > 0) {
 #pragma unroll
-                    for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
-                        const float t = fmaf(esig, se_reg[e], ea);
-                        rs = fmaf(erow[e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rs);
-                    }
+                    for (int e = 0; e < (PT > 0 ? PT : 1); ++e)
+                        rs = fmaf(lds_f(a_el + e * ELB), ex2_approx(fminf((ve_reg[e] - e_me) * nbs, 0.0f)), rs);
                 } else {
-                    for (int e = 0; e < P; ++e) {
-                        const float t = fmaf(esig, mir[32 + e], ea);
-                        rs = fmaf(erow[e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rs);
-                    }
+                    for (int e = 0; e < P; ++e)
+                        rs = fmaf(lds_f(a_el + e * ELB), ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f)), rs);
                 }
                 pre = scan_d((double)rs);
                 if (K > 0) {
-                    cache[slot * 32 + lane] = pre;
-                    if (lane == 0) keys[slot] = occ;
-                    valid |= 1u << slot;
+                    sts_d(a_cache + slot * 256 + lane * 8, pre);
+                    if (lane == 0) sts_u(a_keys + slot * 4, occ);
                 }
             }
             const double total = __shfl_sync(FULL, pre, 31);
-            if (!(total > 0.0)) {  // no transition possible (simulation.go:297 would divide by zero)
+            if (__any_sync(FULL, !(total > 0.0))) {  // no transition possible (simulation.go:297 would divide by zero)
                 dead = true;
                 break;
             }
@@ -229,15 +293,16 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             double r_pick;
             double dtd = 0.0;
             if (!inject) {
-                const uint2 rv = rngbuf[q];
+                const uint2 rv = lds_u2(a_rng + q * 8);
                 const float dt = __uint_as_float(rv.x) * rcp_approx((float)total);
                 t_part += dt;
                 if (DBG) dtd = (double)dt;
                 const double ts = total * 2.3283064365386963e-10;
                 r_pick = fma((double)rv.y, ts, 0.5 * ts);
             } else {
-                dtd = E.stream_e[m * total_hops + h0 + q] / total;          // simulation.go:297
-                r_pick = (double)E.stream_u[m * total_hops + h0 + q] * total;  // simulation.go:164
+                const int64_t hh = h + (q - q0);
+                dtd = E.stream_e[m * total_hops + hh] / total;          // simulation.go:297
+                r_pick = (double)E.stream_u[m * total_hops + hh] * total;  // simulation.go:164
                 t_acc += dtd;
             }
 
@@ -248,7 +313,7 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             const double pprev = __shfl_sync(FULL, pre, istar > 0 ? istar - 1 : 0);
             const float rf = (float)(r_pick - (istar > 0 ? pprev : 0.0));
             const bool rowocc = (occ >> istar) & 1u;
-            const float s_star = mir[istar];
+            const float e_star = lds_f(a_mir + istar * 4);
 
             // ---- second level: re-evaluate the winning lane's targets lane-parallel
             int from, to;
@@ -261,8 +326,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 if (emp) {  // acceptor targets: istar -> empty `lane`
                     float rr = 0.0f;
                     if ((emp >> lane) & 1u) {
-                        const float2 v = col_acc[istar];
-                        rr = v.x * ex2_approx(fminf(fmaf(v.y, pb, s_me - s_star), 0.0f));
+                        const float2 v = lds_f2(a_col_me + istar * 8);
+                        rr = ma(v.x, v.y, e_me, e_star, nb);
                     }
                     const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
                     if (nz) {
@@ -277,28 +342,24 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 }
                 if (to < 0) {  // electrode targets: istar -> electrode `lane`
                     float rr = 0.0f;
-                    if (lane < P) rr = col_el[istar].x * ex2_approx(fminf(se_mine - s_star, 0.0f));
+                    if (lane < P) rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
                     const int e = pick_group<ESTEPS>(rr, rf - sA);
                     to = (e >= 0) ? N + e : lastA;  // electrode group empty (rounding): last acceptor target
-                }
-                if (to < 0) {
-                    dead = true;
-                    break;
                 }
             } else {  // empty acceptor: events electrode `lane` -> istar
                 to = istar;
                 float rr = 0.0f;
-                if (lane < P) rr = col_el[istar].y * ex2_approx(fminf(s_star - se_mine, 0.0f));
-                const int e = pick_group<ESTEPS>(rr, rf);
-                if (e < 0) {
-                    dead = true;
-                    break;
-                }
-                from = N + e;
+                if (lane < P) rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
+                from = pick_group<ESTEPS>(rr, rf);
+                if (from >= 0) from += N;
+            }
+            if (to < 0 || from < 0) {
+                dead = true;
+                break;
             }
 
             // ---- tallies (simulation.go:309-317: pre-hop occupation, antisymmetric traffic)
-            if (DBG && h0 + q >= E.prehops) {
+            if (DBG && h >= prehops) {
                 if ((occ >> lane) & 1u) occtime += dtd;
                 if (lane == 0) {
                     if (E.traffic) {
@@ -307,7 +368,7 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                         tr[to * S + from] -= 1.0;
                     }
                     if (E.trace) {
-                        int32_t *tp = E.trace + (m * E.hops + (h0 + q - E.prehops)) * 2;
+                        int32_t *tp = E.trace + (m * E.hops + (h + (q - q0) - prehops)) * 2;
                         tp[0] = from;
                         tp[1] = to;
                     }
@@ -315,14 +376,22 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             }
 
             // ---- apply the hop (simulation.go:107-130)
+            eoc += (int)(lane == to - N) - (int)(lane == from - N);
             if (from < N) {
                 occ &= ~(1u << from);
-                eps64 -= (double)row_me[from * PITCH].y;
-            } else if (lane == from - N) eoc -= 1;
+                eps64 -= (double)lds_f2(a_row_me + from * ROWB).y;
+            }
             if (to < N) {
                 occ |= (1u << to);
-                eps64 += (double)row_me[to * PITCH].y;
-            } else if (lane == to - N) eoc += 1;
+                eps64 += (double)lds_f2(a_row_me + to * ROWB).y;
+            }
+        }
+        h = hend;
+        if (h == prehops && prehops > 0 && !dead) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
+            t_acc = 0.0;
+            t_part = 0.0f;
+            eoc = 0;
+            occtime = 0.0;
         }
     }
 
@@ -336,18 +405,53 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
         if (DBG && E.avg_occupation) E.avg_occupation[m * N + lane] = occtime;
         if (E.site_energies_out) E.site_energies_out[m * S + lane] = eps64;
     }
-    if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)(float)E.electrode_v[m * P + lane];
+    if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)ve_mine;
     if (DBG && E.misses && lane == 0) E.misses[m] = n_miss;
+}
+
+// ---- parity probe: energies + dense rate matrix of one state with the production arithmetic
+__global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, const double *electrode_v, float kT,
+                                 const uint8_t *occ, float *se_io, int se_given, float *rates) {
+    const int N = L.N, S = L.S, pitch = L.pitchf;
+    const int lane = threadIdx.x;
+    if (!se_given) {
+        for (int i = lane; i < S; i += 32) {
+            double e = (i < N) ? (double)(float)E_constant[i] : (double)(float)electrode_v[i - N];
+            if (i < N)
+                for (int j = 0; j < N; ++j)
+                    if (!occ[j]) e -= (double)L.tblf[j * pitch + i].y;
+            se_io[i] = (float)e;
+        }
+    }
+    __syncwarp();
+    const float nb = -1.4426950408889634f / kT;
+    for (int idx = lane; idx < S * S; idx += 32) {
+        const int i = idx / S, j = idx % S;
+        bool ok = (i != j) && !(i >= N && j >= N);
+        if (ok && i < N) ok = occ[i] != 0;
+        if (ok && j < N) ok = occ[j] == 0;
+        float r = 0.0f;
+        if (ok) {
+            if (i < N && j < N) {
+                const float2 v = L.tblf[j * pitch + i];
+                r = ma(v.x, v.y, se_io[j], se_io[i], nb);
+            } else if (i < N) {  // i -> electrode j
+                r = L.tblf[j * pitch + i].x * ex2_approx(fminf((se_io[j] - se_io[i]) * nb, 0.0f));
+            } else {             // electrode i -> acceptor j
+                r = L.tblf[i * pitch + j].y * ex2_approx(fminf((se_io[j] - se_io[i]) * nb, 0.0f));
+            }
+        }
+        rates[idx] = r;
+    }
 }
 
 template <int PT, int LOGK>
 static cudaError_t launch_memo_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
-    constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
-    constexpr int WARP_BYTES = 256 + 512 + (K > 4 ? K * 4 : 16) + K * 256;
+    using G = MemoGeom<LOGK>;
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e || E.misses;
     int warps = 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
-    const size_t smem = (((size_t)L.S * 33 * sizeof(float2) + 15) & ~size_t(15)) + (size_t)warps * WARP_BYTES;
+    const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     const unsigned grid = (unsigned)((E.B + warps - 1) / warps);
     auto kern = dbg ? kmc_memo_kernel<PT, LOGK, true> : kmc_memo_kernel<PT, LOGK, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -370,10 +474,17 @@ static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int l
 // logk: log2(cache slots per warp); -1 disables the memoisation (same code path, every hop a miss)
 cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches) {
     if (E.B <= 0) return cudaSuccess;
-    if (L.N > 32 || L.P > 32) return cudaErrorInvalidValue;
+    if (L.N > 32 || L.P > 32 || L.pitchf != 33) return cudaErrorInvalidValue;
     if (L.P == 8) return launch_memo_p<8>(L, E, logk, st, launches);
     if (L.P == 2) return launch_memo_p<2>(L, E, logk, st, launches);
     return launch_memo_p<0>(L, E, logk, st, launches);
+}
+
+cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,
+                         const uint8_t *occ, float *se_io, int se_given, float *rates, cudaStream_t st, int *launches) {
+    kmc_probe_kernel<<<1, 32, 0, st>>>(L, E_constant, electrode_v, (float)kT, occ, se_io, se_given, rates);
+    if (launches) ++*launches;
+    return cudaGetLastError();
 }
 
 }  // namespace kmcb200

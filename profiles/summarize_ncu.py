@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Turns an `ncu --set full --import-source on` report into the text summary committed under profiles/.
+
+    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep <total hops in the profiled launch> > profiles/<name>.txt
+"""
+import collections
+import csv
+import io
+import subprocess
+import sys
+
+WANT = [
+    "gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_warps",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__inst_executed.avg.per_cycle_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max",
+    "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+]
+STALLS = "smsp__average_warps_issue_stalled_"
+
+
+def ncu(args):
+    return subprocess.run(["ncu"] + args, capture_output=True, text=True).stdout
+
+
+def main():
+    rep, hops = sys.argv[1], float(sys.argv[2])
+    raw = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
+    hdr, units, vals = raw[0], raw[1], raw[2]
+    kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+    print(f"kernel: {kname}")
+    print(f"hops in this launch: {hops:.6g}")
+    d = dict(zip(hdr, zip(units, vals)))
+    for k in WANT:
+        if k in d:
+            print(f"{k:90s} {d[k][1]:>16s} {d[k][0]}")
+    stalls = sorted(((float(v[1].replace(",", "")), k) for k, v in d.items() if k.startswith(STALLS) and k.endswith("_per_warp_active.pct")
+                     ), reverse=True)[:8]
+    for v, k in stalls:
+        print(f"stall {k[len(STALLS):-len('_per_warp_active.pct')]:40s} {v:8.2f} %")
+    if "smsp__inst_executed.sum" in d:
+        inst = float(d["smsp__inst_executed.sum"][1].replace(",", ""))
+        print(f"warp-instructions per hop: {inst / hops:.1f}")
+    if "gpu__time_duration.sum" in d:
+        t = float(d["gpu__time_duration.sum"][1].replace(",", ""))
+        u = d["gpu__time_duration.sum"][0]
+        t *= {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}.get(u, 1e-9)
+        print(f"hops/s under the profiler (serialised, cold): {hops / t:.4g}")
+    src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv"]))))
+    h2 = src[1]
+    isrc, iex = h2.index("Source"), h2.index("Instructions Executed")
+    hist = collections.Counter()
+    for r in src[2:]:
+        t = r[isrc].strip().split()
+        if not t:
+            continue
+        op = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
+        hist[op.split(".")[0]] += int(r[iex])
+    print("SASS opcode mix, warp-instructions per hop:")
+    print("  " + ", ".join(f"{op} {c / hops:.1f}" for op, c in hist.most_common(30)))
+
+
+if __name__ == "__main__":
+    main()
