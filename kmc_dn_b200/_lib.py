@@ -42,7 +42,7 @@ _PRUNED = [C.c_longlong, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_d
 EXPORTS = ["wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlus", "wrapperSimulatePruned",
            "parallelSimulations", "kmcb200_device_count", "kmcb200_last_error", "kmcb200_version",
            "kmcb200_set_seed", "kmcb200_layout_create", "kmcb200_layout_destroy", "kmcb200_run_ensemble",
-           "kmcb200_probe_rates", "kmcb200_launch_count", "kmcb200_sizeof_ensemble_args"]
+           "kmcb200_probe_rates", "kmcb200_launch_count", "kmcb200_sizeof_ensemble_args", "kmcb200_measure_peak"]
 
 _lib = None
 
@@ -76,6 +76,8 @@ def load():
                                         C.c_int, C.c_void_p]
     lib.kmcb200_probe_rates.restype = C.c_int
     lib.kmcb200_launch_count.restype = C.c_longlong
+    lib.kmcb200_measure_peak.argtypes = [C.c_int, C.c_int]
+    lib.kmcb200_measure_peak.restype = C.c_double
     lib.kmcb200_sizeof_ensemble_args.restype = C.c_int
     if lib.kmcb200_sizeof_ensemble_args() != C.sizeof(EnsembleArgs):
         raise RuntimeError("kmcb200_ensemble_args layout mismatch between libkmcb200.so and kmc_dn_b200/_lib.py")

@@ -22,6 +22,7 @@ UNITS = {
     "hop_reforder.cu": [],
     "hop_exact.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "kmc_api.cu": [],
+    "peaks.cu": [],
 }
 DEPS = ["kmc_internal.cuh", "kmc_device.cuh", os.path.join("..", "..", "include", "kmc_b200.h")]
 

@@ -60,19 +60,23 @@ __device__ __forceinline__ int pick_in_group(float rr, float thr, int lane) {
     return bal ? (__ffs(bal) - 1) : (31 - __clz(nz));
 }
 
-template <int AS, int PT, bool DBG>
+template <int AS, int PT, bool DBG, bool GT>
 __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const EnsembleDev E) {
     constexpr int PITCH = 32 * AS + 1;
     constexpr int MIRW = 32 * AS + 32;  // per-warp mirror: acceptor energies [0,32*AS), electrode energies after
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *tbl = reinterpret_cast<float2 *>(smem_raw);
+    // GT: the pair table stays in global memory (L1/L2-resident; N > 64: 2*S^2 floats exceed shared memory)
+    const float2 *tbl = GT ? L.tblf : reinterpret_cast<const float2 *>(smem_raw);
     const int N = L.N, S = L.S;
     const int P = PT > 0 ? PT : L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    float *mir_base = reinterpret_cast<float *>(tbl + S * PITCH);
+    float *mir_base = reinterpret_cast<float *>(smem_raw + (GT ? 0 : (size_t)S * PITCH * sizeof(float2)));
     uint2 *rng_base = reinterpret_cast<uint2 *>(mir_base + nwarps * MIRW);
 
-    for (int idx = tid; idx < S * PITCH; idx += blockDim.x) tbl[idx] = L.tblf[idx];
+    if (!GT) {
+        float2 *stage = reinterpret_cast<float2 *>(smem_raw);
+        for (int idx = tid; idx < S * PITCH; idx += blockDim.x) stage[idx] = L.tblf[idx];
+    }
     __syncthreads();
 
     const int64_t m = (int64_t)blockIdx.x * nwarps + warp;
@@ -402,17 +406,17 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
     if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)(float)E.electrode_v[m * P + lane];
 }
 
-template <int AS, int PT>
+template <int AS, int PT, bool GT>
 static cudaError_t launch_fast_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e;
     // warps per CTA: large enough to amortise the table copy, small enough to balance small ensembles
-    int warps = 8;
+    int warps = AS >= 4 ? 4 : 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
     const int threads = warps * 32;
-    const size_t smem = (size_t)L.S * (32 * AS + 1) * sizeof(float2) + (size_t)warps * (32 * AS + 32) * sizeof(float) +
-                        (size_t)warps * 64 * sizeof(uint2);
+    const size_t smem = (GT ? 0 : (size_t)L.S * (32 * AS + 1) * sizeof(float2)) +
+                        (size_t)warps * (32 * AS + 32) * sizeof(float) + (size_t)warps * 64 * sizeof(uint2);
     const unsigned grid = (unsigned)((E.B + warps - 1) / warps);
-    auto kern = dbg ? kmc_fast_kernel<AS, PT, true> : kmc_fast_kernel<AS, PT, false>;
+    auto kern = dbg ? kmc_fast_kernel<AS, PT, true, GT> : kmc_fast_kernel<AS, PT, false, GT>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     kern<<<grid, threads, smem, st>>>(L, E);
@@ -420,18 +424,22 @@ static cudaError_t launch_fast_t(const LayoutDev &L, const EnsembleDev &E, cudaS
     return cudaGetLastError();
 }
 
+// N <= 256 acceptors.  (N <= 32 normally runs the memoised kernel of hop_memo.cu; this one is the general path.)
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
     if (E.B <= 0) return cudaSuccess;
     const int as = (L.N + 31) / 32;
+    if (L.pitchf != 32 * (as == 3 ? 4 : (as > 4 ? 8 : as)) + 1) return cudaErrorInvalidValue;
     if (as <= 1) {
-        if (L.P == 8) return launch_fast_t<1, 8>(L, E, st, launches);
-        if (L.P == 2) return launch_fast_t<1, 2>(L, E, st, launches);
-        return launch_fast_t<1, 0>(L, E, st, launches);
+        if (L.P == 8) return launch_fast_t<1, 8, false>(L, E, st, launches);
+        if (L.P == 2) return launch_fast_t<1, 2, false>(L, E, st, launches);
+        return launch_fast_t<1, 0, false>(L, E, st, launches);
     }
     if (as == 2) {
-        if (L.P == 8) return launch_fast_t<2, 8>(L, E, st, launches);
-        return launch_fast_t<2, 0>(L, E, st, launches);
+        if (L.P == 8) return launch_fast_t<2, 8, false>(L, E, st, launches);
+        return launch_fast_t<2, 0, false>(L, E, st, launches);
     }
+    if (as <= 4) return launch_fast_t<4, 0, true>(L, E, st, launches);
+    if (as <= 8) return launch_fast_t<8, 0, true>(L, E, st, launches);
     return cudaErrorInvalidValue;
 }
 

@@ -60,6 +60,13 @@ extern "C" void kmcb200_set_seed(uint64_t seed) {
     g_next_member.store(0);
 }
 extern "C" long long kmcb200_launch_count(void) { return g_launches.load(); }
+extern "C" double kmcb200_measure_peak(int device, int what) {
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    int launches = 0;
+    const double r = measure_peak(what, &launches);
+    g_launches += launches;
+    return r;
+}
 
 // ---------------------------------------------------------------- layout
 template <typename T>
@@ -124,8 +131,11 @@ extern "C" kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const
             tbl[(size_t)j * D.pitch2 + i] = v;
         }
     // production table: acceptor sources only
-    D.pitchf = 32 * ((N + 31) / 32) + 1;
-    if (N == 0) D.pitchf = 33;
+    {   // acceptor row slots per lane of the general kernel: 1, 2, 4 or 8
+        int as = (N + 31) / 32;
+        as = as <= 1 ? 1 : (as == 2 ? 2 : (as <= 4 ? 4 : 8));
+        D.pitchf = 32 * as + 1;
+    }
     std::vector<float2> tblf((size_t)S * D.pitchf, make_float2(0.f, 0.f));
     for (int j = 0; j < S; ++j)
         for (int i = 0; i < N; ++i) {
@@ -180,8 +190,8 @@ static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     const bool warp_kernel = a->mode == KMCB200_MODE_FAST || a->mode == KMCB200_MODE_FAST_REFORDER;
     if (warp_kernel && ((a->stream_e != nullptr) != (a->stream_u != nullptr)))
         return fail("kmcb200_run_ensemble: stream_e and stream_u come together");
-    if (a->mode == KMCB200_MODE_FAST && lay->dev.N > 64)
-        return fail("kmcb200_run_ensemble: fast kernel supports N <= 64 acceptors in this build");
+    if (a->mode == KMCB200_MODE_FAST && lay->dev.N > 256)
+        return fail("kmcb200_run_ensemble: fast kernel supports N <= 256 acceptors in this build");
     if (a->mode == KMCB200_MODE_FAST_REFORDER && lay->dev.S > 64)
         return fail("kmcb200_run_ensemble: reference-order kernel supports N+P <= 64");
     if (lay->dev.P > 32) return fail("kmcb200_run_ensemble: more than 32 electrodes unsupported");

@@ -50,4 +50,6 @@ cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const dou
                          const uint8_t *occ, float *se_io, int se_given, float *rates_out, cudaStream_t st,
                          int *launches);
 
+double measure_peak(int what, int *launches);
+
 }  // namespace kmcb200

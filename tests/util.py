@@ -55,3 +55,24 @@ def go_stream(seed, hops):
     e = rng.standard_exponential(hops)
     u = rng.random(hops, dtype=np.float32)
     return e, u
+
+
+def synthetic_layout(N, P, seed, kT=1.0, I_0=100.0, a=0.25, fill=0.8):
+    """Uniform-random 2-D layout with P electrodes on the boundary (shape of examples/scaling.py); E_constant is a
+    smooth synthetic potential.  Same keys as the golden cases."""
+    rng = np.random.default_rng(seed)
+    acc = np.zeros((N, 3)); acc[:, :2] = rng.random((N, 2))
+    el = np.zeros((P, 4))
+    for p in range(P):
+        t = (p // 4 + 1) / (P // 4 + 2) if P > 4 else 0.5
+        el[p, :2] = [(0.0, t), (1.0, t), (t, 0.0), (t, 1.0)][p % 4]
+        el[p, 3] = rng.uniform(-30, 30)
+    pos = np.vstack([acc, el[:, :3]])
+    d = np.sqrt(((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1))
+    R = N ** -0.5
+    tc = np.exp(-2 * d / (a * R)) - np.eye(N + P)
+    w = np.exp(-4 * ((acc[:, None, :2] - el[None, :, :2]) ** 2).sum(-1))
+    E = (w * el[None, :, 3]).sum(1) / np.maximum(w.sum(1), 1e-9) + rng.normal(0, 3, N)
+    occ = rng.random(N) < fill
+    return dict(N=N, P=P, nu=1.0, kT=kT, I_0=I_0, R=R, distances=d, transitions_constant=tc, E_constant=E,
+                electrode_v=el[:, 3].copy(), occupation=occ)
