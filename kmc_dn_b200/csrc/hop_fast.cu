@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
     const int N = L.N, S = L.S;
     const int P = PT > 0 ? PT : L.P;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    float *mir_base = reinterpret_cast<float *>(smem_raw + (GT ? 0 : (size_t)S * PITCH * sizeof(float2)));
+    float *mir_base = reinterpret_cast<float *>(smem_raw + (GT ? 0 : (((size_t)S * PITCH * sizeof(float2) + 15) & ~size_t(15))));
     uint2 *rng_base = reinterpret_cast<uint2 *>(mir_base + nwarps * MIRW);
 
     if (!GT) {
@@ -413,7 +413,7 @@ static cudaError_t launch_fast_t(const LayoutDev &L, const EnsembleDev &E, cudaS
     int warps = AS >= 4 ? 4 : 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
     const int threads = warps * 32;
-    const size_t smem = (GT ? 0 : (size_t)L.S * (32 * AS + 1) * sizeof(float2)) +
+    const size_t smem = (GT ? 0 : (((size_t)L.S * (32 * AS + 1) * sizeof(float2) + 15) & ~size_t(15))) +
                         (size_t)warps * (32 * AS + 32) * sizeof(float) + (size_t)warps * 64 * sizeof(uint2);
     const unsigned grid = (unsigned)((E.B + warps - 1) / warps);
     auto kern = dbg ? kmc_fast_kernel<AS, PT, true, GT> : kmc_fast_kernel<AS, PT, false, GT>;

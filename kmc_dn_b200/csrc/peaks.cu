@@ -2,7 +2,7 @@
 // bounded by (SURVEY.md section 8d asks for measured denominators: MEASURED_PEAKS.json only has HBM and bf16).
 //   what = 0: MUFU.EX2 throughput (ex2.approx per second, all SMs)
 //   what = 1: FP32 FFMA throughput (fma per second)
-//   what = 2: warp-instruction issue rate (independent IADD3 chains; warp-instructions per second)
+//   what = 2: warp-instruction issue rate (FFMA + LOP3 mix on both FP/INT pipes; warp-instructions per second)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -23,9 +23,12 @@ __global__ void __launch_bounds__(256) peak_kernel(float *sink, int iters) {
             FMA(a0); FMA(a1); FMA(a2); FMA(a3); FMA(a4); FMA(a5); FMA(a6); FMA(a7);
 #undef FMA
         } else {
-#define IAD(x) asm volatile("add.s32 %0, %0, 3;" : "+r"(x))
-            IAD(i0); IAD(i1); IAD(i2); IAD(i3); IAD(i4); IAD(i5); IAD(i6); IAD(i7);
-#undef IAD
+            // 4 FFMA (fma pipe) + 4 XOR in a rotating dependency ring (alu pipe): nothing ptxas can fold
+#define FMA(x) asm volatile("fma.rn.f32 %0, %0, %0, %0;" : "+f"(x))
+#define XR(x, y) asm volatile("xor.b32 %0, %0, %1;" : "+r"(x) : "r"(y))
+            FMA(a0); XR(i0, i1); FMA(a1); XR(i1, i2); FMA(a2); XR(i2, i3); FMA(a3); XR(i3, i0);
+#undef FMA
+#undef XR
         }
     }
     const float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + (float)(i0 + i1 + i2 + i3 + i4 + i5 + i6 + i7);

@@ -522,3 +522,25 @@ def test_boltzmann_statistics_without_electrodes():
     mean, sem = frac.mean(0), frac.std(0) / np.sqrt(B)
     assert np.all(np.abs(mean - exact) < 5 * sem + 1e-3), (mean, exact)
     assert abs(mean.sum() - n_holes) < 1e-6
+
+
+def test_generation_fitness_in_one_launch(fixtures_subset):
+    """a whole generation (candidates x logic-table tests x seeds) evaluated as one ensemble equals
+    evaluating every (candidate, test) separately, and the reduction is the reference's error function."""
+    from kmc_dn_b200 import workloads
+    from kmc_dn_b200.ensemble import Layout
+    from kmc_dn_b200.search_eval import error_corr, evaluate_generation, generation_members
+    w = workloads.c3_voltage_search(n_controls=4, seeds=1, hops=1000)
+    lt = w["tables"]
+    tests = [((0, 0), False), ((0, 75), True), ((75, 0), True), ((75, 75), False)]
+    rng = np.random.default_rng(4)
+    controls = rng.uniform(-150, 150, (6, 5))
+    lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R)
+    errs, cur = evaluate_generation(lay, lt.basis, controls, tests, hops=20000, seeds=4, seed=9, occupation0=w["occupation0"])
+    assert errs.shape == (6,) and cur.shape == (6, 4) and np.isfinite(errs).all()
+    V = generation_members(controls, tests, 8, seeds=4)
+    r = lay.run(20000, 1.0, V, E_constant=lt.E_constant(V), seed=9, occupation0=w["occupation0"])
+    lay.close()
+    np.testing.assert_allclose(r["current"][:, 7].reshape(6, 4, 4).mean(2), cur, rtol=1e-6, atol=1e-12)
+    for g in range(6):
+        assert errs[g] == pytest.approx(error_corr(cur[g], tests))

@@ -121,3 +121,29 @@ def test_workload_builders_are_deterministic_and_shaped():
         assert (w["tables"].N, w["tables"].P) == shape and len(w["V"]) == len(w["kT"])
     w = workloads.c5_scaling(N=64, M=6, B=16)
     assert w["tables"].S == 72
+
+
+def test_search_error_function_matches_reference_formula():
+    """voltage_search.py:118-136 on hand-checked inputs."""
+    from kmc_dn_b200.search_eval import error_corr, generation_members, perfect_correlation
+    tests = [((0, 0), False), ((0, 75), True), ((75, 0), True), ((75, 75), False)]  # XOR (voltage_search_tests.py:159)
+    np.testing.assert_array_equal(perfect_correlation(tests), [0, 10, 10, 0])
+    # separated: highest_false (max(-1, 0.1, 0.2)) - lowest_true (min(1, 0.5, 0.6)) = -0.3, corr = 0.9734...
+    vals = [0.1, 0.5, 0.6, 0.2]
+    corr = np.corrcoef([0, 10, 10, 0], vals)[0][1]
+    assert error_corr(vals, tests) == pytest.approx(corr * (0.2 - 0.5))
+    assert error_corr(vals, tests, corr_pow=3) == pytest.approx(corr ** 3 * (0.2 - 0.5))
+    # not separated: positive separation is returned as is
+    assert error_corr([0.4, 0.1, 0.6, 0.2], tests) == pytest.approx(0.4 - 0.1)
+    # anti-correlated: corr clamps to 0
+    assert error_corr([0.5, -0.2, -0.1, 0.6], tests) == pytest.approx(0.6 - (-0.2))
+    assert error_corr([0.0, -0.2, -0.1, -0.3], tests) == pytest.approx(0.0 - (-0.2))
+    # currents far below the initial bounds (1, -1): highest_false stays -1 only if every false current < -1
+    assert error_corr([-2.0, 3.0, 4.0, -5.0], tests) == pytest.approx(1.0 * (-1 - 1) * np.corrcoef([0, 10, 10, 0], [-2, 3, 4, -5])[0][1])
+    V = generation_members(np.array([[1., 2, 3, 4, 5], [6, 7, 8, 9, 10]]), tests, 8, seeds=3)
+    assert V.shape == (2 * 4 * 3, 8)
+    np.testing.assert_array_equal(V[0], [0, 0, 1, 2, 3, 4, 5, 0])
+    np.testing.assert_array_equal(V[3], [0, 75, 1, 2, 3, 4, 5, 0])   # seeds are the fastest index
+    np.testing.assert_array_equal(V[-1], [75, 75, 6, 7, 8, 9, 10, 0])
+    with pytest.raises(ValueError):
+        generation_members(np.zeros((1, 4)), tests, 8)
