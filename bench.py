@@ -340,7 +340,12 @@ def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device):
                       "note": "warp-instructions/hop from the committed ncu capture of this kernel (profiles/)"},
             "hbm": {"achieved_gbs": hbm_achieved, "peak_gbs": hbm_peak, "frac": hbm_achieved / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-            "traffic": ncu.get("dram_bytes_per_launch"), "sample": stats}
+            "traffic": (B * (ncu["dram_bytes_read_per_member"] + ncu["dram_bytes_written_per_member"])
+                        if "dram_bytes_read_per_member" in ncu else None),
+            "traffic_note": "dram__bytes_read+write of the ncu capture, scaled per member to this launch; algorithmic "
+                            f"bytes per member = {bytes_per_member} (inputs {8 * lt.P + 8 + lt.N} B, outputs {8 + 8 * lt.P} B; "
+                            "the outputs stay in the 126 MB L2 until the D2H copy)",
+            "sample": stats}
 
 
 if __name__ == "__main__":

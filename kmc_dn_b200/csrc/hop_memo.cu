@@ -65,6 +65,11 @@ __device__ __forceinline__ uint2 lds_u2(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ double lds_d(uint32_t a) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -133,7 +138,7 @@ template <int LOGK>
 struct MemoGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
     static constexpr int KEYB = K > 4 ? K * 4 : 16;
-    static constexpr int WARP_BYTES = 256 + 512 + KEYB + K * 256;  // mirror | variates | keys | prefixes
+    static constexpr int WARP_BYTES = 256 + 1024 + KEYB + K * 256;  // mirror | variates | keys | prefixes
 };
 
 template <int PT, int LOGK, bool DBG>
@@ -166,7 +171,7 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
-    const uint32_t a_mir = wb, a_rng = wb + 256, a_keys = wb + 768, a_cache = wb + 768 + G::KEYB;
+    const uint32_t a_mir = wb, a_rng = wb + 256, a_keys = wb + 1280, a_cache = wb + 1280 + G::KEYB;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
@@ -221,6 +226,11 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     bool dead = false;
     long long n_miss = 0;
 
+    uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
+    uint32_t key_spec = ~occ;  // first hop: miss
+    double pre_spec = 0.0;
+    __syncwarp();
+
     int64_t h = 0;
     while (h < total_hops && !dead) {
         // a chunk never straddles a 64-hop variate block or the prehops boundary
@@ -235,10 +245,14 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             t_part = 0.0f;
             const uint64_t blk = (uint64_t)(h >> 6) * 32u + (uint64_t)lane;
             const uint4 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), key);
+            // per hop: a unit exponential (float) for the dwell time and a uniform in (0,1) (double, (x+0.5)/2^32)
             const float e0 = -0.6931471805599453f * lg2_approx(fmaf((float)r.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
             const float e1 = -0.6931471805599453f * lg2_approx(fmaf((float)r.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+            const double u0 = ((double)r.y + 0.5) * 2.3283064365386963e-10;
+            const double u1 = ((double)r.w + 0.5) * 2.3283064365386963e-10;
             __syncwarp();
-            sts_u4(a_rng + lane * 16, make_uint4(__float_as_uint(e0), r.y, __float_as_uint(e1), r.w));
+            sts_u4(a_rng + lane * 32, make_uint4(__float_as_uint(e0), 0u, (uint32_t)__double2loint(u0), (uint32_t)__double2hiint(u0)));
+            sts_u4(a_rng + lane * 32 + 16, make_uint4(__float_as_uint(e1), 0u, (uint32_t)__double2loint(u1), (uint32_t)__double2hiint(u1)));
         }
         for (int q = q0; q < q1; ++q) {
             // ---- publish the fp32 energies
@@ -247,14 +261,12 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             sts_f(a_mir + lane * 4, e_me);
             __syncwarp();
 
-            // ---- cumulative structure of this state: cached or computed
-            double pre;
-            const uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
+            // ---- cumulative structure of this state: cached or computed.  The key and this lane's prefix entry
+            //      were fetched speculatively when the previous hop was applied (software pipelining of the lookup).
+            double pre = pre_spec;
             bool hit = false;
-            if (K > 0) hit = __all_sync(FULL, lds_u(a_keys + slot * 4) == occ);
-            if (hit) {
-                pre = lds_d(a_cache + slot * 256 + lane * 8);
-            } else {
+            if (K > 0) hit = __all_sync(FULL, key_spec == occ);
+            if (!hit) {
                 if (DBG) ++n_miss;
                 const bool o = (occ >> lane) & 1u;
                 const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
@@ -284,21 +296,16 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 }
             }
             const double total = __shfl_sync(FULL, pre, 31);
-            if (__any_sync(FULL, !(total > 0.0))) {  // no transition possible (simulation.go:297 would divide by zero)
-                dead = true;
-                break;
-            }
 
             // ---- random variates
             double r_pick;
             double dtd = 0.0;
             if (!inject) {
-                const uint2 rv = lds_u2(a_rng + q * 8);
+                const uint4 rv = lds_u4(a_rng + q * 16);
                 const float dt = __uint_as_float(rv.x) * rcp_approx((float)total);
                 t_part += dt;
                 if (DBG) dtd = (double)dt;
-                const double ts = total * 2.3283064365386963e-10;
-                r_pick = fma((double)rv.y, ts, 0.5 * ts);
+                r_pick = __hiloint2double((int)rv.w, (int)rv.z) * total;
             } else {
                 const int64_t hh = h + (q - q0);
                 dtd = E.stream_e[m * total_hops + hh] / total;          // simulation.go:297
@@ -308,7 +315,15 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
 
             // ---- first level: the lane
             uint32_t bal = __ballot_sync(FULL, pre >= r_pick);
-            if (!bal) bal = __ballot_sync(FULL, pre >= total);  // threshold rounded past the end: last positive lane
+            if (!bal) {
+                bal = __ballot_sync(FULL, pre >= total);  // threshold rounded past the end: last positive lane
+                if (!bal) {                               // NaN structure
+                    dead = true;
+                    break;
+                }
+            }
+            // (total == 0, no transition possible -- simulation.go:297 would divide by zero -- selects lane 0 here
+            //  and is caught below: no target has a positive rate)
             const int istar = __ffs(bal) - 1;
             const double pprev = __shfl_sync(FULL, pre, istar > 0 ? istar - 1 : 0);
             const float rf = (float)(r_pick - (istar > 0 ? pprev : 0.0));
@@ -384,6 +399,11 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             if (to < N) {
                 occ |= (1u << to);
                 eps64 += (double)lds_f2(a_row_me + to * ROWB).y;
+            }
+            if (K > 0) {  // prefetch the next state's cache line
+                slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
+                key_spec = lds_u(a_keys + slot * 4);
+                pre_spec = lds_d(a_cache + slot * 256 + lane * 8);
             }
         }
         h = hend;
