@@ -23,7 +23,8 @@
 // energies are exact.  Every warp keeps a direct-mapped cache in shared memory:
 //
 //     key   = 32-bit occupation mask              (slot = multiplicative hash, 2^LOGK slots)
-//     value = the fp64 inclusive prefix over the 32 lane sums (256 B: one double per lane, lane-private column)
+//     value = the fp64 exclusive prefix over the 32 lane sums (one double per lane, lane-private column),
+//             the fp64 total and its fp32 reciprocal (272 B per state)
 //
 // Hit:  the sweep and the fp64 scan are skipped; the hop costs the lookup, the first-level ballot, the
 //       second-level re-evaluation of ONE lane's targets and the state update.
@@ -31,7 +32,7 @@
 // Memoising a pure function cannot change a result: with the cache disabled (LOGK = -1 instantiation,
 // KMCB200_FLAG_NO_MEMO) the kernel produces bit-identical trajectories (tests/test_gpu_parity.py).
 // The reference's cache stores the full per-pair list per state (up to 150e6 floats per trajectory); here the
-// second level is recomputed instead of stored, so 256 B per state keeps 16 states per warp on chip.
+// second level is recomputed instead of stored, so 272 B per state keep 16 states per warp on chip.
 //
 // Shared-memory accesses in the hop loop go through explicit ld/st.shared on 32-bit shared addresses: every
 // branch condition is then provably warp-uniform for the compiler (votes), and no generic-address arithmetic
@@ -138,7 +139,8 @@ template <int LOGK>
 struct MemoGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
     static constexpr int KEYB = K > 4 ? K * 4 : 16;
-    static constexpr int WARP_BYTES = 256 + 1024 + KEYB + K * 256;  // mirror | variates | keys | prefixes
+    static constexpr int ENTRY = 272;  // 32 x f64 exclusive prefix | f64 total | f32 1/total | pad
+    static constexpr int WARP_BYTES = 256 + 1024 + KEYB + K * ENTRY;  // mirror | variates | keys | entries
 };
 
 template <int PT, int LOGK, bool DBG>
@@ -228,7 +230,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
 
     uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
     uint32_t key_spec = ~occ;  // first hop: miss
-    double pre_spec = 0.0;
+    double pre_spec = 0.0, tot_spec = 0.0;
+    float rcp_spec = 0.0f;
     __syncwarp();
 
     int64_t h = 0;
@@ -263,7 +266,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
 
             // ---- cumulative structure of this state: cached or computed.  The key and this lane's prefix entry
             //      were fetched speculatively when the previous hop was applied (software pipelining of the lookup).
-            double pre = pre_spec;
+            double pre = pre_spec, total = tot_spec;  // pre = EXCLUSIVE prefix of this lane
+            float rtot = rcp_spec;
             bool hit = false;
             if (K > 0) hit = __all_sync(FULL, key_spec == occ);
             if (!hit) {
@@ -289,20 +293,27 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                     for (int e = 0; e < P; ++e)
                         rs = fmaf(lds_f(a_el + e * ELB), ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f)), rs);
                 }
-                pre = scan_d((double)rs);
+                const double incl = scan_d((double)rs);
+                total = __shfl_sync(FULL, incl, 31);
+                pre = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix: an empty lane can never win
+                if (lane == 0) pre = 0.0;
+                rtot = rcp_approx((float)total);
                 if (K > 0) {
-                    sts_d(a_cache + slot * 256 + lane * 8, pre);
-                    if (lane == 0) sts_u(a_keys + slot * 4, occ);
+                    sts_d(a_cache + slot * G::ENTRY + lane * 8, pre);
+                    if (lane == 0) {
+                        sts_d(a_cache + slot * G::ENTRY + 256, total);
+                        sts_f(a_cache + slot * G::ENTRY + 264, rtot);
+                        sts_u(a_keys + slot * 4, occ);
+                    }
                 }
             }
-            const double total = __shfl_sync(FULL, pre, 31);
 
             // ---- random variates
             double r_pick;
             double dtd = 0.0;
             if (!inject) {
                 const uint4 rv = lds_u4(a_rng + q * 16);
-                const float dt = __uint_as_float(rv.x) * rcp_approx((float)total);
+                const float dt = __uint_as_float(rv.x) * rtot;
                 t_part += dt;
                 if (DBG) dtd = (double)dt;
                 r_pick = __hiloint2double((int)rv.w, (int)rv.z) * total;
@@ -313,20 +324,14 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 t_acc += dtd;
             }
 
-            // ---- first level: the lane
-            uint32_t bal = __ballot_sync(FULL, pre >= r_pick);
-            if (!bal) {
-                bal = __ballot_sync(FULL, pre >= total);  // threshold rounded past the end: last positive lane
-                if (!bal) {                               // NaN structure
-                    dead = true;
-                    break;
-                }
+            // ---- first level: the lane = the highest one whose interval starts below the threshold
+            const uint32_t bal = __ballot_sync(FULL, pre < r_pick);
+            if (!bal) {  // total == 0 (no transition possible; simulation.go:297 would divide by zero) or NaN
+                dead = true;
+                break;
             }
-            // (total == 0, no transition possible -- simulation.go:297 would divide by zero -- selects lane 0 here
-            //  and is caught below: no target has a positive rate)
-            const int istar = __ffs(bal) - 1;
-            const double pprev = __shfl_sync(FULL, pre, istar > 0 ? istar - 1 : 0);
-            const float rf = (float)(r_pick - (istar > 0 ? pprev : 0.0));
+            const int istar = 31 - __clz(bal);
+            const float rf = __shfl_sync(FULL, (float)(r_pick - pre), istar);
             const bool rowocc = (occ >> istar) & 1u;
             const float e_star = lds_f(a_mir + istar * 4);
 
@@ -391,19 +396,24 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             }
 
             // ---- apply the hop (simulation.go:107-130)
-            eoc += (int)(lane == to - N) - (int)(lane == from - N);
             if (from < N) {
                 occ &= ~(1u << from);
                 eps64 -= (double)lds_f2(a_row_me + from * ROWB).y;
+            } else {
+                eoc -= (int)(lane == from - N);
             }
             if (to < N) {
                 occ |= (1u << to);
                 eps64 += (double)lds_f2(a_row_me + to * ROWB).y;
+            } else {
+                eoc += (int)(lane == to - N);
             }
             if (K > 0) {  // prefetch the next state's cache line
                 slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
                 key_spec = lds_u(a_keys + slot * 4);
-                pre_spec = lds_d(a_cache + slot * 256 + lane * 8);
+                pre_spec = lds_d(a_cache + slot * G::ENTRY + lane * 8);
+                tot_spec = lds_d(a_cache + slot * G::ENTRY + 256);
+                rcp_spec = lds_f(a_cache + slot * G::ENTRY + 264);
             }
         }
         h = hend;
