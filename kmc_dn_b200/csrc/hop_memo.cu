@@ -229,9 +229,10 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     long long n_miss = 0;
 
     uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-    uint32_t key_spec = ~occ;  // first hop: miss
-    double pre_spec = 0.0, tot_spec = 0.0;
-    float rcp_spec = 0.0f;
+    // loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied
+    uint32_t keyv = ~occ;  // first hop: miss
+    double pre = 0.0, total = 0.0;  // pre = EXCLUSIVE prefix of this lane
+    float rtot = 0.0f;
     __syncwarp();
 
     int64_t h = 0;
@@ -264,12 +265,10 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             sts_f(a_mir + lane * 4, e_me);
             __syncwarp();
 
-            // ---- cumulative structure of this state: cached or computed.  The key and this lane's prefix entry
-            //      were fetched speculatively when the previous hop was applied (software pipelining of the lookup).
-            double pre = pre_spec, total = tot_spec;  // pre = EXCLUSIVE prefix of this lane
-            float rtot = rcp_spec;
+            // ---- cumulative structure of this state: cached or computed.  The key and this lane's entry were
+            //      fetched speculatively when the previous hop was applied (software pipelining of the lookup).
             bool hit = false;
-            if (K > 0) hit = __all_sync(FULL, key_spec == occ);
+            if (K > 0) hit = __all_sync(FULL, keyv == occ);
             if (!hit) {
                 if (DBG) ++n_miss;
                 const bool o = (occ >> lane) & 1u;
@@ -410,10 +409,10 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             }
             if (K > 0) {  // prefetch the next state's cache line
                 slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-                key_spec = lds_u(a_keys + slot * 4);
-                pre_spec = lds_d(a_cache + slot * G::ENTRY + lane * 8);
-                tot_spec = lds_d(a_cache + slot * G::ENTRY + 256);
-                rcp_spec = lds_f(a_cache + slot * G::ENTRY + 264);
+                keyv = lds_u(a_keys + slot * 4);
+                pre = lds_d(a_cache + slot * G::ENTRY + lane * 8);
+                total = lds_d(a_cache + slot * G::ENTRY + 256);
+                rtot = lds_f(a_cache + slot * G::ENTRY + 264);
             }
         }
         h = hend;
