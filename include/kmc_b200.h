@@ -66,6 +66,14 @@ double wrapperSimulateRecordPlus(long long NSites, long long NElectrodes, double
                                  GoSlice electrode_occupation, GoSlice site_energies, int hops,
                                  unsigned char record, GoSlice traffic,
                                  GoSlice average_occupation);      /* simulationWrapper.go:149-169 */
+double wrapperSimulateProbability(long long NSites, long long NElectrodes, double nu, double kT,
+                                  double I_0, double R, double time_unused, GoSlice occupation,
+                                  GoSlice distances, GoSlice E_constant, GoSlice transitions_constant,
+                                  GoSlice electrode_occupation, GoSlice site_energies, int hops,
+                                  unsigned char record, GoSlice traffic,
+                                  GoSlice average_occupation);     /* simulationWrapper.go:218-233: mean-field
+                                     solver; WRITES the fractional occupations into `occupation` and the acceptor
+                                     energies into `site_energies`, as the Go code does                      */
 /* extra leading prune_threshold (simulationWrapper.go:98-110, pythonBind.py:73-79) */
 double wrapperSimulatePruned(long long NSites, long long NElectrodes, double prune_threshold, double nu,
                              double kT, double I_0, double R, double time_unused, GoSlice occupation,
@@ -102,8 +110,11 @@ enum {
     KMCB200_MODE_GO_SIMULATE = 1,   /* replay: op-for-op simulate,           simulation.go:194-325     */
     KMCB200_MODE_GO_RECORDPLUS = 2, /* replay: op-for-op simulateRecordPlus, simulation.go:327-432     */
     KMCB200_MODE_PY = 3,            /* replay: op-for-op numba loop, kmc_dopant_networks.py:33-135     */
-    KMCB200_MODE_FAST_REFORDER = 4  /* production arithmetic with the reference's row-major event order:
+    KMCB200_MODE_FAST_REFORDER = 4, /* production arithmetic with the reference's row-major event order:
                                        follows the Go loop hop for hop under an injected stream           */
+    KMCB200_MODE_PROB = 5           /* mean-field pre-screen probSimulate, probabilitySimulation.go:53-157
+                                       (deterministic, fp64; `hops` = relaxation steps; occupation starts
+                                       at 0.5; results in prob_occupation / prob_electrode_occ / time)    */
 };
 
 enum {
@@ -144,6 +155,8 @@ typedef struct {
     int32_t *trace;             /* [B,hops,2] or NULL: (from,to) of every recorded hop                 */
     int64_t *misses;            /* [B] or NULL: hops whose rate structure had to be evaluated (MODE_FAST:
                                    state-cache misses; equals prehops+hops with KMCB200_FLAG_NO_MEMO)     */
+    double *prob_occupation;    /* [B,N] or NULL: fractional occupations (MODE_PROB)                   */
+    double *prob_electrode_occ; /* [B,P] or NULL: fractional electrode tallies (MODE_PROB)             */
     void *stream;               /* cudaStream_t, NULL = default stream                                 */
 } kmcb200_ensemble_args;
 

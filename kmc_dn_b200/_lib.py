@@ -11,7 +11,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libkmcb200.so")
 
-MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER = 0, 1, 2, 3, 4
+MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER, MODE_PROB = 0, 1, 2, 3, 4, 5
 FLAG_DEVICE_PTRS = 1
 FLAG_NO_MEMO = 2
 
@@ -30,7 +30,8 @@ class EnsembleArgs(C.Structure):
         ("stream_e", C.c_void_p), ("stream_u", C.c_void_p), ("stream_u64", C.c_void_p),
         ("time", C.c_void_p), ("electrode_occ", C.c_void_p), ("occupation_out", C.c_void_p),
         ("site_energies_out", C.c_void_p), ("avg_occupation", C.c_void_p), ("traffic", C.c_void_p),
-        ("trace", C.c_void_p), ("misses", C.c_void_p), ("stream", C.c_void_p),
+        ("trace", C.c_void_p), ("misses", C.c_void_p), ("prob_occupation", C.c_void_p),
+        ("prob_electrode_occ", C.c_void_p), ("stream", C.c_void_p),
     ]
 
 
@@ -40,6 +41,7 @@ _PRUNED = [C.c_longlong, C.c_longlong, C.c_double, C.c_double, C.c_double, C.c_d
            GoSlice, GoSlice, GoSlice, GoSlice, GoSlice, GoSlice, C.c_int, C.c_bool, GoSlice, GoSlice]
 
 EXPORTS = ["wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlus", "wrapperSimulatePruned",
+           "wrapperSimulateProbability",
            "parallelSimulations", "kmcb200_device_count", "kmcb200_last_error", "kmcb200_version",
            "kmcb200_set_seed", "kmcb200_layout_create", "kmcb200_layout_destroy", "kmcb200_run_ensemble",
            "kmcb200_probe_rates", "kmcb200_launch_count", "kmcb200_sizeof_ensemble_args", "kmcb200_measure_peak"]
@@ -56,7 +58,7 @@ def load():
         raise RuntimeError(f"{SO_PATH} is missing: build it with `python -m kmc_dn_b200.build` "
                            "(kmc_dn_b200 has no CPU fallback)")
     lib = C.CDLL(SO_PATH)
-    for name in ("wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlus"):
+    for name in ("wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlus", "wrapperSimulateProbability"):
         f = getattr(lib, name); f.argtypes = _SINGLE; f.restype = C.c_double
     lib.wrapperSimulatePruned.argtypes = _PRUNED
     lib.wrapperSimulatePruned.restype = C.c_double

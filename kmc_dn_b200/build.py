@@ -21,6 +21,7 @@ UNITS = {
     "hop_memo.cu": [],
     "hop_reforder.cu": [],
     "hop_exact.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
+    "hop_prob.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "kmc_api.cu": [],
     "peaks.cu": [],
 }

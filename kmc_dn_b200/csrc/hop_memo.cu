@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             } else {
                 eoc += (int)(lane == to - N);
             }
-            if (K > 0) {  // prefetch the next state's cache line
+            if (K > 0) {  // prefetch the next state's cache line (lane 0 may have written it in this very hop)
+                __syncwarp();
                 slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
                 keyv = lds_u(a_keys + slot * 4);
                 pre = lds_d(a_cache + slot * G::ENTRY + lane * 8);

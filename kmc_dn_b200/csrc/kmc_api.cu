@@ -180,10 +180,13 @@ size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");
     if (a->B < 0 || a->hops < 0 || a->prehops < 0) return fail("kmcb200_run_ensemble: negative size");
-    if (a->mode < 0 || a->mode > 4) return fail("kmcb200_run_ensemble: unknown mode");
+    if (a->mode < 0 || a->mode > 5) return fail("kmcb200_run_ensemble: unknown mode");
     if (!a->E_constant && !(a->basis && a->electrode_v)) return fail("kmcb200_run_ensemble: need E_constant or basis+electrode_v");
     if (lay->dev.P > 0 && !a->electrode_v) return fail("kmcb200_run_ensemble: electrode_v is required");
-    if (!a->kT || !a->time || !a->electrode_occ) return fail("kmcb200_run_ensemble: kT/time/electrode_occ are required");
+    if (!a->kT || !a->time) return fail("kmcb200_run_ensemble: kT/time are required");
+    if (a->mode != KMCB200_MODE_PROB && !a->electrode_occ) return fail("kmcb200_run_ensemble: electrode_occ is required");
+    if (a->mode == KMCB200_MODE_PROB && (a->flags & KMCB200_FLAG_DEVICE_PTRS) && a->traffic)
+        return fail("kmcb200_run_ensemble: MODE_PROB traffic needs host pointers");
     if (a->mode == KMCB200_MODE_PY && !a->stream_u64) return fail("kmcb200_run_ensemble: MODE_PY replays an injected stream (stream_u64)");
     if ((a->mode == KMCB200_MODE_GO_SIMULATE || a->mode == KMCB200_MODE_GO_RECORDPLUS) && !(a->stream_e && a->stream_u))
         return fail("kmcb200_run_ensemble: Go replay modes need stream_e and stream_u");
@@ -208,7 +211,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     const int N = D.N, P = D.P, S = D.S;
     const int64_t B = a->B, H = a->prehops + a->hops;
     const bool dev_ptrs = a->flags & KMCB200_FLAG_DEVICE_PTRS;
-    const bool exact = a->mode != KMCB200_MODE_FAST && a->mode != KMCB200_MODE_FAST_REFORDER;
+    const bool prob = a->mode == KMCB200_MODE_PROB;
+    const bool exact = !prob && a->mode != KMCB200_MODE_FAST && a->mode != KMCB200_MODE_FAST_REFORDER;
 
     EnsembleDev E{};
     E.B = B; E.hops = a->hops; E.prehops = a->prehops; E.mode = a->mode;
@@ -216,7 +220,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
 
     // workspace sizing
     size_t need = 0;
-    const size_t scratch_bytes = exact ? a256(sizeof(double) * (size_t)B * S * S) : 0;
+    const size_t scratch_bytes = (exact || (prob && a->traffic)) ? a256(sizeof(double) * (size_t)B * S * S) : 0;
     need += scratch_bytes;
     if (!dev_ptrs) {
         if (a->E_constant) need += a256(sizeof(double) * B * N);
@@ -234,6 +238,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         if (a->traffic) need += a256(sizeof(double) * (size_t)B * S * S);
         if (a->trace) need += a256(sizeof(int32_t) * (size_t)B * a->hops * 2);
         if (a->misses) need += a256(sizeof(int64_t) * B);
+        if (a->prob_occupation) need += a256(sizeof(double) * B * N);
+        if (a->prob_electrode_occ) need += a256(sizeof(double) * B * P);
     }
     if (need > lay->ws_bytes) {
         if (lay->ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ws)); lay->ws = nullptr; lay->ws_bytes = 0; }
@@ -241,7 +247,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         lay->ws_bytes = need;
     }
     Carver cv{(char *)lay->ws};
-    if (exact) E.scratch = cv.take<double>((size_t)B * S * S);
+    if (scratch_bytes) E.scratch = cv.take<double>((size_t)B * S * S);
 
     if (dev_ptrs) {
         E.E_constant = a->E_constant; E.basis = a->basis; E.electrode_v = a->electrode_v; E.kT = a->kT;
@@ -250,6 +256,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         E.site_energies_out = a->site_energies_out; E.avg_occupation = a->avg_occupation; E.traffic = a->traffic;
         E.trace = a->trace;
         E.misses = (long long *)a->misses;
+        E.prob_occupation = a->prob_occupation; E.prob_electrode_occ = a->prob_electrode_occ;
         if (E.traffic) CU(cudaMemsetAsync(E.traffic, 0, sizeof(double) * (size_t)B * S * S, st));
     } else {
 #define H2D(field, T, count)                                                                          \
@@ -268,7 +275,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         H2D(stream_u64, double, (size_t)B * 2 * H)
 #undef H2D
         E.time = cv.take<double>(B);
-        E.electrode_occ = cv.take<int64_t>((size_t)B * P);
+        if (a->electrode_occ) E.electrode_occ = cv.take<int64_t>((size_t)B * P);
         if (a->occupation_out) E.occupation_out = cv.take<uint8_t>((size_t)B * N);
         if (a->site_energies_out) E.site_energies_out = cv.take<double>((size_t)B * S);
         if (a->avg_occupation) E.avg_occupation = cv.take<double>((size_t)B * N);
@@ -278,11 +285,14 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         }
         if (a->trace) E.trace = cv.take<int32_t>((size_t)B * a->hops * 2);
         if (a->misses) E.misses = cv.take<long long>(B);
+        if (a->prob_occupation) E.prob_occupation = cv.take<double>((size_t)B * N);
+        if (a->prob_electrode_occ) E.prob_electrode_occ = cv.take<double>((size_t)B * P);
     }
 
     int launches = 0;
     cudaError_t le;
-    if (exact) le = launch_exact(D, E, st, &launches);
+    if (prob) le = launch_prob(D, E, st, &launches);
+    else if (exact) le = launch_exact(D, E, st, &launches);
     else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
     else if (D.N <= 32 && !getenv("KMCB200_NO_MEMO_KERNEL")) {
         int logk = 4;
@@ -304,6 +314,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         D2H(traffic, double, (size_t)B * S * S)
         D2H(trace, int32_t, (size_t)B * a->hops * 2)
         D2H(misses, int64_t, (size_t)B)
+        D2H(prob_occupation, double, (size_t)B * N)
+        D2H(prob_electrode_occ, double, (size_t)B * P)
 #undef D2H
         CU(cudaStreamSynchronize(st));
     }
@@ -432,6 +444,38 @@ extern "C" double wrapperSimulateRecordPlus(long long NSites, long long NElectro
     // record is forced off (simulationWrapper.go:164-165)
     return run_single("wrapperSimulateRecordPlus", NSites, NElectrodes, 0.0, nu, kT, I_0, R, distances, E_constant,
                       transitions_constant, electrode_occupation, site_energies, hops, false, traffic, average_occupation);
+}
+extern "C" double wrapperSimulateProbability(long long NSites, long long NElectrodes, double nu, double kT, double I_0, double R,
+                                             double, GoSlice occupation, GoSlice distances, GoSlice E_constant,
+                                             GoSlice transitions_constant, GoSlice electrode_occupation,
+                                             GoSlice site_energies, int hops, unsigned char record, GoSlice traffic,
+                                             GoSlice average_occupation) {
+    // mean-field pre-screen (simulationWrapper.go:218-233 -> probabilitySimulation.go:53-157); occupation and the
+    // acceptor entries of site_energies are written back, as the Go code does through the shared slices
+    const char *name = "wrapperSimulateProbability";
+    const int N = (int)NSites, P = (int)NElectrodes, S = N + P;
+    if (distances.len < (long long)S * S || transitions_constant.len < (long long)S * S || E_constant.len < N ||
+        site_energies.len < S || electrode_occupation.len < P || occupation.len < N) {
+        fail("slice shorter than NSites/NElectrodes imply");
+        die(name);
+    }
+    kmcb200_layout *lay = cached_layout(N, P, distances.data, transitions_constant.data, nu, I_0, R, 0.0);
+    if (!lay) die(name);
+    double time = 0.0;
+    std::vector<double> se(S > 0 ? S : 1, 0.0);
+    kmcb200_ensemble_args a;
+    memset(&a, 0, sizeof(a));
+    a.B = 1; a.hops = hops; a.mode = KMCB200_MODE_PROB;
+    a.E_constant = E_constant.data; a.electrode_v = site_energies.data + N; a.kT = &kT;
+    a.time = &time; a.prob_occupation = occupation.data; a.prob_electrode_occ = electrode_occupation.data;
+    a.site_energies_out = se.data();
+    if (record) {
+        if (traffic.data && traffic.len >= (long long)S * S) a.traffic = traffic.data;
+        if (average_occupation.data && average_occupation.len >= N) a.avg_occupation = average_occupation.data;
+    }
+    if (kmcb200_run_ensemble(lay, &a)) die(name);
+    for (int i = 0; i < N; ++i) site_energies.data[i] = se[i];
+    return time;
 }
 extern "C" double wrapperSimulatePruned(long long NSites, long long NElectrodes, double prune_threshold, double nu, double kT,
                                         double I_0, double R, double, GoSlice, GoSlice distances, GoSlice E_constant,

@@ -38,6 +38,7 @@ struct EnsembleDev {
     double *time; int64_t *electrode_occ; uint8_t *occupation_out; double *site_energies_out;
     double *avg_occupation; double *traffic; int32_t *trace;
     long long *misses;  // [B] rate-structure evaluations (cache misses) per member, or null
+    double *prob_occupation, *prob_electrode_occ;  // MODE_PROB: fractional occupations [B,N], electrode tallies [B,P]
     double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
 };
 
@@ -45,6 +46,7 @@ struct EnsembleDev {
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches);
 cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
+cudaError_t launch_prob(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,
                          const uint8_t *occ, float *se_io, int se_given, float *rates_out, cudaStream_t st,

@@ -10,7 +10,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER,  # noqa: F401
+from ._lib import (MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER, MODE_PROB,  # noqa: F401
                    FLAG_DEVICE_PTRS, FLAG_NO_MEMO)
 
 
@@ -129,6 +129,32 @@ class Layout:
         a.stream = cuda_stream
         if self.lib.kmcb200_run_ensemble(self._h, C.byref(a)):
             raise RuntimeError("kmcb200_run_ensemble: " + _lib.last_error())
+
+    def run_prob(self, steps, kT, electrode_v, E_constant=None, basis=None, record=False):
+        """Mean-field pre-screen (probSimulate, goSimulation/probabilitySimulation.go:53-157) for B members:
+        `steps` relaxation steps from occupation 0.5.  Returns time[B], occupation[B,N] (fractional),
+        electrode_occupation[B,P] (fractional), current, and with record: traffic, avg_occupation."""
+        N, P, S = self.N, self.P, self.S
+        V = _host(np.atleast_2d(electrode_v), np.float64)
+        B = V.shape[0] if P > 0 else np.atleast_2d(E_constant).shape[0]
+        kTa = _host(np.broadcast_to(np.asarray(kT, dtype=np.float64), (B,)), np.float64)
+        Ec = None if E_constant is None else _host(np.atleast_2d(E_constant), np.float64)
+        bs = None if basis is None else _host(basis, np.float64)
+        out = dict(time=np.zeros(B), occupation=np.zeros((B, N)), electrode_occupation=np.zeros((B, P)),
+                   site_energies=np.zeros((B, S)))
+        if record:
+            out["avg_occupation"] = np.zeros((B, N)); out["traffic"] = np.zeros((B, S, S))
+        a = _lib.EnsembleArgs()
+        a.B, a.hops, a.prehops, a.mode, a.flags = B, int(steps), 0, MODE_PROB, 0
+        a.E_constant, a.basis, a.electrode_v, a.kT = _ptr(Ec), _ptr(bs), _ptr(V), _ptr(kTa)
+        a.time, a.prob_occupation, a.prob_electrode_occ = _ptr(out["time"]), _ptr(out["occupation"]), _ptr(out["electrode_occupation"])
+        a.site_energies_out = _ptr(out["site_energies"])
+        a.avg_occupation, a.traffic = _ptr(out.get("avg_occupation")), _ptr(out.get("traffic"))
+        if self.lib.kmcb200_run_ensemble(self._h, C.byref(a)):
+            raise RuntimeError("kmcb200_run_ensemble: " + _lib.last_error())
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out["current"] = out["electrode_occupation"] / out["time"][:, None]
+        return out
 
     def probe_rates(self, E_constant, electrode_v, kT, occupation, site_energies=None):
         """fp32 energies and dense rate matrix of one state with the fast kernel's arithmetic."""

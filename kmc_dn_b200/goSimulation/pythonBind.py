@@ -12,7 +12,8 @@ import numpy as np
 from .. import _lib
 from .._lib import GoSlice, goslice  # noqa: F401  (GoSlice re-exported like the reference module)
 
-_SYMBOLS = ("wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlus", "wrapperSimulatePruned")
+_SYMBOLS = ("wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlus", "wrapperSimulatePruned",
+            "wrapperSimulateProbability")
 
 
 def _f64(a):

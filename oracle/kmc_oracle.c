@@ -537,3 +537,85 @@ int kmc_oracle_py_ensemble(int N, int P, int64_t B, double nu, const double *kT,
     J.seed0 = seed0; J.time_out = time_out; J.eo_out_i64 = electrode_occ_out;
     return ens_run(&J, nthreads);
 }
+
+/* ===================================================================== (C) */
+/*
+ * kmc_oracle_prob -- restatement of the mean-field "probability" solver probSimulate
+ * (goSimulation/probabilitySimulation.go:53-157, calcProbTransitions :8-38, probTransitionPossible :40-50)
+ * behind wrapperSimulateProbability (simulationWrapper.go:218-233: fp64 tables, occupation forced to 0.5).
+ * Deterministic (no random numbers), fp64 throughout, same loop order as the reference.
+ *   occupation   f64[N] out (fractional occupations after `hops` relaxation steps; starts at 0.5)
+ *   electrode_occ f64[P] out;  site_energies f64[S] in ([N:]) / out ([:N])
+ *   traffic f64[S*S], average_occupation f64[N]: accumulated when record (caller zeroes)
+ * returns the accumulated time.
+ */
+double kmc_oracle_prob(int NSites, int NElectrodes, double nu, double kT, double I_0, double R,
+                       double *occupation, const double *distances, const double *E_constant,
+                       const double *transitions_constant, double *electrode_occupation,
+                       double *site_energies, int64_t hops, int record, double *traffic,
+                       double *average_occupation)
+{
+    const int N = NSites + NElectrodes;
+    double *transitions = (double *)calloc((size_t)N * N, sizeof(double));
+    double *difference = (double *)calloc(NSites > 0 ? NSites : 1, sizeof(double));
+    for (int j = 0; j < NSites; j++) occupation[j] = 0.5;             /* simulationWrapper.go:226-228 */
+    for (int i = 0; i < NElectrodes; i++) electrode_occupation[i] = 0.0;
+    double time = 0.0, tot_rates = 0.0;
+    for (int64_t hop = 0; hop < hops; hop++) {
+        for (int i = 0; i < NSites; i++) {                            /* :84-93 */
+            difference[i] = 0;
+            double acc = 0.0;
+            for (int j = 0; j < NSites; j++)
+                if (j != i) acc += (1 - occupation[j]) / distances[i * N + j];
+            site_energies[i] = E_constant[i] - I_0 * R * acc;
+        }
+        tot_rates = 0.0;                                              /* calcProbTransitions :8-38 */
+        for (int i = 0; i < N; i++)
+            for (int j = 0; j < N; j++) {
+                double base;
+                if (i >= NSites && j >= NSites) base = 0;
+                else if (i >= NSites) base = 1 - occupation[j];
+                else if (j >= NSites) base = occupation[i];
+                else base = (1 - occupation[j]) * occupation[i];
+                double dE;
+                if (i < NSites && j < NSites) dE = site_energies[j] - site_energies[i] - I_0 * R / distances[i * N + j];
+                else dE = site_energies[j] - site_energies[i];
+                double t = (dE > 0) ? base * nu * exp(-dE / kT) : base * nu;
+                t *= transitions_constant[i * N + j];
+                transitions[i * N + j] = t;
+                tot_rates += t;
+                if (i < NSites) difference[i] -= t;
+                if (j < NSites) difference[j] += t;
+            }
+        double max_change = 1.0;                                      /* :99-114 */
+        for (int i = 0; i < NSites; i++) {
+            const double newVal = occupation[i] + difference[i] / tot_rates;
+            if (newVal < 0) {
+                const double req = occupation[i] / -(difference[i] / tot_rates);
+                if (req < max_change) max_change = req;
+            }
+            if (newVal > 1) {
+                const double req = (1 - occupation[i]) / (difference[i] / tot_rates);
+                if (req < max_change) max_change = req;
+            }
+        }
+        const double time_step = 0.98 * max_change / tot_rates;
+        time += time_step;
+        if (record && average_occupation)
+            for (int i = 0; i < NSites; i++) average_occupation[i] += occupation[i] * time_step;
+        for (int i = 0; i < N; i++)                                   /* :123-145 */
+            for (int j = 0; j < N; j++) {
+                if (i >= NSites && j >= NSites) break;
+                const double rate = transitions[i * N + j] * max_change / tot_rates;
+                if (i < NSites) occupation[i] -= rate; else electrode_occupation[i - NSites] -= rate;
+                if (j < NSites) occupation[j] += rate; else electrode_occupation[j - NSites] += rate;
+                if (record && traffic) { traffic[i * N + j] += rate; traffic[j * N + i] -= rate; }
+            }
+        for (int i = 0; i < NSites; i++) {                            /* :146-155 */
+            if (occupation[i] < 0) occupation[i] = 0;
+            if (occupation[i] > 1) occupation[i] = 1;
+        }
+    }
+    free(transitions); free(difference);
+    return time;
+}

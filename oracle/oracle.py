@@ -148,3 +148,18 @@ def py_ensemble(N, P, nu, kT, I_0, R, distances, E_constant, transitions_constan
                                         _p(_c64(transitions_constant)), _p(V), C.c_int64(hops),
                                         C.c_uint64(seed0), C.c_int(nthreads), _p(time), _p(eo))
     return dict(time=time, electrode_occupation=eo, threads=used)
+
+
+def prob_simulate(N, P, nu, kT, I_0, R, distances, E_constant, transitions_constant, site_energies, hops, record=False):
+    """Mean-field solver probSimulate (goSimulation/probabilitySimulation.go:53-157) behind
+    wrapperSimulateProbability (simulationWrapper.go:218-233)."""
+    S = N + P
+    occ = np.zeros(max(N, 1)); eo = np.zeros(max(P, 1)); se = _c64(site_energies).copy()
+    traffic = np.zeros((S, S)) if record else None
+    avg = np.zeros(max(N, 1)) if record else None
+    lib().kmc_oracle_prob.restype = C.c_double
+    t = lib().kmc_oracle_prob(C.c_int(N), C.c_int(P), C.c_double(nu), C.c_double(kT), C.c_double(I_0), C.c_double(R),
+                              _p(occ), _p(_c64(distances)), _p(_c64(E_constant)), _p(_c64(transitions_constant)), _p(eo),
+                              _p(se), C.c_int64(hops), C.c_int(int(record)), _p(traffic), _p(avg))
+    return dict(time=t, occupation=occ[:N], electrode_occupation=eo[:P], site_energies=se, traffic=traffic,
+                average_occupation=None if avg is None else avg[:N])

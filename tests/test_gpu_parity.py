@@ -544,3 +544,43 @@ def test_generation_fitness_in_one_launch(fixtures_subset):
     np.testing.assert_allclose(r["current"][:, 7].reshape(6, 4, 4).mean(2), cur, rtol=1e-6, atol=1e-12)
     for g in range(6):
         assert errs[g] == pytest.approx(error_corr(cur[g], tests))
+
+
+def test_mean_field_prescreen_vs_oracle(golden_py, fixtures_subset):
+    """probSimulate (probabilitySimulation.go:53-157) on the GPU vs its C restatement: time, fractional
+    occupations, electrode tallies, acceptor energies, traffic and occupied time to fp64 rounding; and through the
+    wrapperSimulateProbability export exactly as dn_search's strategy 0 calls it (dn_search.py:49-52)."""
+    from oracle import oracle
+    from kmc_dn_b200.goSimulation.pythonBind import callGoSimulation
+    cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "c2_grid_N16_P8": golden_py["c2_grid_N16_P8"],
+             "n5_p3_hot": golden_py["n5_p3_hot"], "N48_P8": synthetic_layout(48, 8, 1, kT=2.0, I_0=30.0)}
+    for name, c in cases.items():
+        steps = 300
+        o = oracle.prob_simulate(c["N"], c["P"], c["nu"], c["kT"], c["I_0"], c["R"], c["distances"], c["E_constant"],
+                                 c["transitions_constant"], site_energies_of(c), steps, record=True)
+        lay = _layout(c)
+        V = np.stack([c["electrode_v"], c["electrode_v"] * 0.5])
+        E = np.stack([c["E_constant"], c["E_constant"]])
+        r = lay.run_prob(steps, c["kT"], V, E_constant=E, record=True)
+        lay.close()
+        assert r["time"][0] == pytest.approx(o["time"], rel=1e-9), name
+        np.testing.assert_allclose(r["occupation"][0], o["occupation"], rtol=1e-8, atol=1e-10, err_msg=name)
+        np.testing.assert_allclose(r["electrode_occupation"][0], o["electrode_occupation"], rtol=1e-7, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(r["site_energies"][0], o["site_energies"], rtol=1e-9, atol=1e-9, err_msg=name)
+        np.testing.assert_allclose(r["avg_occupation"][0], o["average_occupation"], rtol=1e-8, atol=1e-10, err_msg=name)
+        np.testing.assert_allclose(r["traffic"][0], o["traffic"], rtol=1e-6, atol=1e-8 * np.abs(o["traffic"]).max(), err_msg=name)
+        assert not np.allclose(r["electrode_occupation"][1], r["electrode_occupation"][0])  # members are independent
+    c = golden_py["fx_rnd_min_max_0"]
+    N, P = c["N"], c["P"]
+    o = oracle.prob_simulate(N, P, c["nu"], c["kT"], c["I_0"], c["R"], c["distances"], c["E_constant"],
+                             c["transitions_constant"], site_energies_of(c), 1000)
+    t, occ, eo = callGoSimulation(N_acceptors=N, N_electrodes=P, nu=c["nu"], kT=c["kT"], I_0=c["I_0"], R=c["R"], time=0.0,
+                                  occupation=c["occupation"], distances=c["distances"], E_constant=c["E_constant"],
+                                  site_energies=site_energies_of(c), transitions_constant=c["transitions_constant"],
+                                  transitions=np.zeros((N + P, N + P)), problist=np.zeros((N + P) ** 2),
+                                  electrode_occupation=np.zeros(P, dtype=int), hops=1000, record=False,
+                                  goSpecificFunction="wrapperSimulateProbability")
+    assert t == pytest.approx(o["time"], rel=1e-8)
+    # the reference binding truncates the (fractional) results to int (pythonBind.py:83-84)
+    np.testing.assert_array_equal(eo, o["electrode_occupation"].astype(np.int64))
+    np.testing.assert_array_equal(occ, o["occupation"].astype(np.int64))

@@ -222,3 +222,19 @@ def test_product_fails_loudly_without_gpu():
     d = np.ones((3, 3)); np.fill_diagonal(d, 0)
     with pytest.raises(RuntimeError, match="no CUDA device"):
         Layout(2, 1, d, d)
+
+
+def test_oracle_mean_field_solver_is_sane(golden_py):
+    """probSimulate restatement: conserves carriers (what leaves the electrodes sits on the acceptors), keeps
+    occupations in [0,1], is deterministic, and relaxes toward the KMC steady state's sign pattern."""
+    c = golden_py["fx_rnd_min_max_0"]
+    args = (c["N"], c["P"], c["nu"], c["kT"], c["I_0"], c["R"], c["distances"], c["E_constant"], c["transitions_constant"],
+            site_energies_of(c))
+    a = oracle.prob_simulate(*args, 500, record=True)
+    b = oracle.prob_simulate(*args, 500, record=True)
+    assert a["time"] == b["time"] and (a["occupation"] == b["occupation"]).all()
+    assert (a["occupation"] >= 0).all() and (a["occupation"] <= 1).all()
+    # carriers: sum(occupation) - N/2 == -(sum electrode tallies) up to the clamping at 0/1
+    assert a["occupation"].sum() - c["N"] / 2 == pytest.approx(-a["electrode_occupation"].sum(), abs=1e-6)
+    np.testing.assert_allclose(a["traffic"], -a["traffic"].T, atol=1e-12)
+    assert (a["average_occupation"] <= a["time"] * (1 + 1e-12)).all()
