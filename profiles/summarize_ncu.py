@@ -32,6 +32,8 @@ def ncu(args):
 
 def main():
     rep, hops = sys.argv[1], float(sys.argv[2])
+    json_out = sys.argv[3] if len(sys.argv) > 3 else None
+    members = float(sys.argv[4]) if len(sys.argv) > 4 else None
     raw = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units, vals = raw[0], raw[1], raw[2]
     kname = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
@@ -63,6 +65,34 @@ def main():
             continue
         op = t[1] if t[0].startswith("@") and len(t) > 1 else t[0]
         hist[op.split(".")[0]] += int(r[iex])
+    if json_out:
+        import json
+
+        def num(k):
+            return float(d[k][1].replace(",", "")) if k in d else None
+
+        def byt(k):
+            if k not in d:
+                return None
+            return num(k) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(d[k][0], 1.0)
+        out = {"source": f"{rep} (ncu --set full --clock-control none)", "kernel": kname, "hops_in_capture": hops,
+               "members_in_capture": members, "warp_inst_per_hop": inst / hops,
+               "ipc_per_sm": num("sm__inst_executed.avg.per_cycle_active"),
+               "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "xu_pipe_pct": num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+               "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+               "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+               "lsu_pipe_pct": num("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+               "fp64_pipe_pct": num("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"),
+               "smem_wavefront_pct": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+               "smem_bank_conflict_wavefronts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+               "smem_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+               "registers_per_thread": num("launch__registers_per_thread"),
+               "achieved_occupancy_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active")}
+        if members:
+            out["dram_bytes_read_per_member"] = byt("dram__bytes_read.sum") / members
+            out["dram_bytes_written_per_member"] = byt("dram__bytes_write.sum") / members
+        json.dump(out, open(json_out, "w"), indent=1)
     print("SASS opcode mix, warp-instructions per hop:")
     print("  " + ", ".join(f"{op} {c / hops:.1f}" for op, c in hist.most_common(30)))
 

@@ -593,3 +593,59 @@ def test_mean_field_prescreen_vs_oracle(golden_py, fixtures_subset):
     # the reference binding truncates the (fractional) results to int (pythonBind.py:83-84)
     assert np.abs(eo - o["electrode_occupation"].astype(np.int64)).max() <= 1
     assert np.abs(occ - o["occupation"].astype(np.int64)).max() <= 1
+
+
+def test_host_class_simulation_entry_points(fixtures_subset):
+    """kmc_dn.go_simulation / python_simulation / ensemble_simulation (mirror of kmc_dopant_networks.py:473-618):
+    python_simulation replays the numba loop under numpy's MT19937 stream, so after np.random.seed(s) it must
+    equal the oracle's run on RandomState(s); go_simulation must reproduce the fixture's currents."""
+    from oracle import oracle
+    from kmc_dn_b200.kmc_dopant_networks import kmc_dn
+    f = fixtures_subset["rnd_min_max/test1"]
+    dn = kmc_dn(int(f["N"]), int(f["M"]), 1, 1, 0, electrodes=f["electrodes"], acceptors=f["acceptors"], donors=f["donors"])
+    np.testing.assert_allclose(dn.E_constant, f["E_constant"], atol=2e-11)
+    # --- python_simulation == numba semantics under the same stream
+    dn.occupation = f["occupation"].astype(bool).copy()
+    occ0 = dn.occupation.copy()
+    hops = 1500
+    np.random.seed(77)
+    dn.python_simulation(hops=hops, record=True)
+    u = np.random.RandomState(77).random_sample(2 * hops)
+    se = np.zeros(dn.N + dn.P); se[dn.N:] = dn.electrodes[:, 3]
+    o = oracle.py_simulate(dn.N, dn.P, dn.nu, dn.kT, dn.I_0, dn.R, occ0, dn.distances, dn.E_constant, se,
+                           dn.transitions_constant, np.zeros(dn.P, dtype=np.int64), hops, record=True, u=u)
+    assert (dn.occupation == o["occupation"]).all()
+    assert (dn.electrode_occupation == o["electrode_occupation"]).all()
+    assert dn.time == pytest.approx(o["time"], rel=1e-12)
+    np.testing.assert_array_equal(dn.traffic, o["traffic"])
+    np.testing.assert_allclose(np.asarray(dn.average_occupation) * dn.time, o["occ_time"], rtol=1e-10)
+    np.testing.assert_allclose(dn.current, o["electrode_occupation"] / o["time"], rtol=1e-12)
+    # prehops run first, on the same stream (kmc_dopant_networks.py:580-585)
+    dn.occupation = occ0.copy()
+    np.random.seed(78)
+    dn.python_simulation(hops=500, prehops=300)
+    u = np.random.RandomState(78).random_sample(2 * 800)
+    a = oracle.py_simulate(dn.N, dn.P, dn.nu, dn.kT, dn.I_0, dn.R, occ0, dn.distances, dn.E_constant, se,
+                           dn.transitions_constant, np.zeros(dn.P, dtype=np.int64), 300, u=u[:600])
+    b = oracle.py_simulate(dn.N, dn.P, dn.nu, dn.kT, dn.I_0, dn.R, a["occupation"], dn.distances, dn.E_constant, se,
+                           dn.transitions_constant, np.zeros(dn.P, dtype=np.int64), 500, u=u[600:])
+    assert (dn.occupation == b["occupation"]).all() and (dn.electrode_occupation == b["electrode_occupation"]).all()
+    assert dn.time == pytest.approx(b["time"], rel=1e-12)
+    # --- go_simulation: the default export, statistics of the fixture
+    ref = np.asarray(f["mean_currents"]); big = np.abs(ref) > 0.05 * np.abs(ref).max()
+    curs = []
+    for _ in range(3):
+        dn.go_simulation(hops=1000000)
+        assert dn.electrode_occupation.shape == (8,) and dn.time > 0
+        curs.append(dn.current.copy())
+    np.testing.assert_allclose(np.mean(curs, 0)[big], ref[big], rtol=0.05)
+    with pytest.raises(TypeError):
+        dn.go_simulation(hops=1E5)  # like the reference binding, ctypes' c_int rejects a float (SURVEY 8b)
+    dn.go_simulation(hops=200000, record=True, goSpecificFunction="wrapperSimulate")
+    assert np.asarray(dn.traffic).shape == (38, 38) and len(dn.average_occupation) == 30
+    # --- ensemble_simulation: IV sweep of electrode 0 as one launch; zero bias everywhere -> zero mean current
+    V = np.zeros((8, 8)); V[:, 0] = np.linspace(-100, 100, 8)
+    r = dn.ensemble_simulation(V, hops=50000, prehops=5000, seeds=4, seed=1)
+    assert r["current"].shape == (32, 8) and np.isfinite(r["current"]).all()
+    cur0 = r["current"].reshape(8, 4, 8).mean(1)[:, 0]
+    assert cur0[0] > 0 > cur0[-1] or cur0[0] < 0 < cur0[-1]  # the swept electrode's current changes sign with its bias
