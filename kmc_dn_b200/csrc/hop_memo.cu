@@ -139,7 +139,7 @@ template <int LOGK>
 struct MemoGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
     static constexpr int KEYB = K > 4 ? K * 4 : 16;
-    static constexpr int ENTRY = 272;  // 32 x f64 exclusive prefix | f64 total | f32 1/total | pad
+    static constexpr int ENTRY = 280;  // 32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | u32 posm
     static constexpr int WARP_BYTES = 256 + 1024 + KEYB + K * ENTRY;  // mirror | variates | keys | entries
 };
 
@@ -147,7 +147,6 @@ template <int PT, int LOGK, bool DBG>
 __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = MemoGeom<LOGK>;
     constexpr int K = G::K;
-    constexpr int ESTEPS = (PT > 0 && PT <= 2) ? 1 : (PT > 0 && PT <= 4) ? 2 : (PT > 0 && PT <= 8) ? 3 : 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = L.N, S = L.S;
     const int P = PT > 0 ? PT : L.P;
@@ -196,25 +195,17 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
 
     // ---- initial state
     bool o0 = false;
-    double eps64 = 0.0;
+    double E64 = 0.0;  // E_constant of this lane's acceptor, narrowed to float32 (simulationWrapper.go:50-56)
     if (lane < N) {
         if (E.occupation0) o0 = E.occupation0[m * N + lane] != 0;
-        if (E.E_constant) eps64 = E.E_constant[m * N + lane];
+        if (E.E_constant) E64 = E.E_constant[m * N + lane];
         else {
-            eps64 = E.basis[(int64_t)P * N + lane];
-            for (int p = 0; p < P; ++p) eps64 += E.electrode_v[m * P + p] * E.basis[(int64_t)p * N + lane];
+            E64 = E.basis[(int64_t)P * N + lane];
+            for (int p = 0; p < P; ++p) E64 += E.electrode_v[m * P + p] * E.basis[(int64_t)p * N + lane];
         }
-        eps64 = (double)(float)eps64;  // simulationWrapper.go:50-56 narrows E_constant to float32
+        E64 = (double)(float)E64;
     }
     uint32_t occ = __ballot_sync(FULL, o0);
-    {
-        uint32_t mm = ~occ & accm;
-        while (mm) {
-            const int j = __ffs(mm) - 1;
-            mm &= mm - 1;
-            eps64 -= (double)lds_f2(a_row_me + j * ROWB).y;
-        }
-    }
 
     const uint64_t gm = E.member_index0 + (uint64_t)m;
     const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
@@ -228,11 +219,72 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     bool dead = false;
     long long n_miss = 0;
 
+    // Site energies of the current state, from scratch: E_const - sum over EMPTY j of I0*R/d_ij (simulation.go:226-234).
+    // fp64 sums of fp32 terms in ascending j: exact, hence a pure function of the occupation mask.
+    auto energy_of = [&](uint32_t o) -> double {
+        double e = E64;
+        uint32_t mm = ~o & accm;
+        while (mm) {
+            const int j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            e -= (double)lds_f2(a_row_me + j * ROWB).y;
+        }
+        return e;
+    };
+
+    // Sweep: every allowed pair of the current state exactly once.  Per lane: its LARGEST rate (top, with the
+    // partner site ptn), and the sum of all its other rates (rest).  Publishes the fp32 energies to the mirror.
+    float e_me = 0.0f, top = 0.0f, rest = 0.0f;
+    uint32_t ptn = 0;
+    auto sweep = [&]() {
+        if (DBG) ++n_miss;
+        e_me = (float)energy_of(occ);
+        __syncwarp();
+        sts_f(a_mir + lane * 4, e_me);
+        __syncwarp();
+        const bool o = (occ >> lane) & 1u;
+        const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
+        const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
+        const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
+        top = 0.0f; rest = 0.0f; ptn = 0;
+        uint32_t mm = ~occ & accm;
+        while (mm) {
+            const int j = __ffs(mm) - 1;
+            mm &= mm - 1;
+            const float ej = lds_f(a_mir + j * 4);
+            const float2 v = lds_f2(a_row_me + j * ROWB);
+            const float x = ma(v.x, v.y, ej, src, nb);
+            rest += fminf(x, top);
+            if (x > top) ptn = j;
+            top = fmaxf(x, top);
+        }
+        if (PT > 0) {
+#pragma unroll
+            for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
+                const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((ve_reg[e] - e_me) * nbs, 0.0f));
+                rest += fminf(x, top);
+                if (x > top) ptn = N + e;
+                top = fmaxf(x, top);
+            }
+        } else {
+            for (int e = 0; e < P; ++e) {
+                const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
+                rest += fminf(x, top);
+                if (x > top) ptn = N + e;
+                top = fmaxf(x, top);
+            }
+        }
+    };
+
     uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-    // loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied
+    // Loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied:
+    //   pre   exclusive fp64 prefix over the lanes' TOP rates; its 6 mantissa LSBs carry the lane's partner site
+    //   mtop  total mass of the top events; total = mtop + mass of all other events; rtot = 1/total (fp32)
+    //   posm  lanes whose top rate is positive
     uint32_t keyv = ~occ;  // first hop: miss
-    double pre = 0.0, total = 0.0;  // pre = EXCLUSIVE prefix of this lane
+    double pre = 0.0, mtop = 0.0, total = 0.0;
     float rtot = 0.0f;
+    uint32_t posm = 0;
     __syncwarp();
 
     int64_t h = 0;
@@ -257,51 +309,34 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             __syncwarp();
             sts_u4(a_rng + lane * 32, make_uint4(__float_as_uint(e0), 0u, (uint32_t)__double2loint(u0), (uint32_t)__double2hiint(u0)));
             sts_u4(a_rng + lane * 32 + 16, make_uint4(__float_as_uint(e1), 0u, (uint32_t)__double2loint(u1), (uint32_t)__double2hiint(u1)));
+            __syncwarp();
         }
         for (int q = q0; q < q1; ++q) {
-            // ---- publish the fp32 energies
-            const float e_me = (float)eps64;
-            __syncwarp();
-            sts_f(a_mir + lane * 4, e_me);
-            __syncwarp();
-
-            // ---- cumulative structure of this state: cached or computed.  The key and this lane's entry were
-            //      fetched speculatively when the previous hop was applied (software pipelining of the lookup).
+            // ---- event structure of this state: cached, or computed and parked
             bool hit = false;
             if (K > 0) hit = __all_sync(FULL, keyv == occ);
+            bool swept = false;
             if (!hit) {
-                if (DBG) ++n_miss;
-                const bool o = (occ >> lane) & 1u;
-                const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
-                const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
-                const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
-                float rs = 0.0f;
-                uint32_t mm = ~occ & accm;
-                while (mm) {
-                    const int j = __ffs(mm) - 1;
-                    mm &= mm - 1;
-                    const float ej = lds_f(a_mir + j * 4);
-                    const float2 v = lds_f2(a_row_me + j * ROWB);
-                    rs += ma(v.x, v.y, ej, src, nb);
-                }
-                if (PT > 0) {
+                sweep();
+                swept = true;
+                const double incl = scan_d((double)top);
+                mtop = __shfl_sync(FULL, incl, 31);
+                double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
+                if (lane == 0) ex = 0.0;
+                double rsum = (double)rest;
 #pragma unroll
-                    for (int e = 0; e < (PT > 0 ? PT : 1); ++e)
-                        rs = fmaf(lds_f(a_el + e * ELB), ex2_approx(fminf((ve_reg[e] - e_me) * nbs, 0.0f)), rs);
-                } else {
-                    for (int e = 0; e < P; ++e)
-                        rs = fmaf(lds_f(a_el + e * ELB), ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f)), rs);
-                }
-                const double incl = scan_d((double)rs);
-                total = __shfl_sync(FULL, incl, 31);
-                pre = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix: an empty lane can never win
-                if (lane == 0) pre = 0.0;
+                for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
+                total = mtop + rsum;
                 rtot = rcp_approx((float)total);
+                posm = __ballot_sync(FULL, top > 0.0f);
+                pre = __hiloint2double(__double2hiint(ex), (__double2loint(ex) & ~63) | (int)ptn);
                 if (K > 0) {
                     sts_d(a_cache + slot * G::ENTRY + lane * 8, pre);
                     if (lane == 0) {
-                        sts_d(a_cache + slot * G::ENTRY + 256, total);
-                        sts_f(a_cache + slot * G::ENTRY + 264, rtot);
+                        sts_d(a_cache + slot * G::ENTRY + 256, mtop);
+                        sts_d(a_cache + slot * G::ENTRY + 264, total);
+                        sts_f(a_cache + slot * G::ENTRY + 272, rtot);
+                        sts_u(a_cache + slot * G::ENTRY + 276, posm);
                         sts_u(a_keys + slot * 4, occ);
                     }
                 }
@@ -323,58 +358,93 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 t_acc += dtd;
             }
 
-            // ---- first level: the lane = the highest one whose interval starts below the threshold
-            const uint32_t bal = __ballot_sync(FULL, pre < r_pick);
-            if (!bal) {  // total == 0 (no transition possible; simulation.go:297 would divide by zero) or NaN
-                dead = true;
-                break;
-            }
-            const int istar = 31 - __clz(bal);
-            const float rf = __shfl_sync(FULL, (float)(r_pick - pre), istar);
-            const bool rowocc = (occ >> istar) & 1u;
-            const float e_star = lds_f(a_mir + istar * 4);
-
-            // ---- second level: re-evaluate the winning lane's targets lane-parallel
             int from, to;
-            if (rowocc) {
-                from = istar;
-                to = -1;
-                int lastA = -1;
-                float sA = 0.0f;
-                const uint32_t emp = ~occ & accm;
-                if (emp) {  // acceptor targets: istar -> empty `lane`
-                    float rr = 0.0f;
-                    if ((emp >> lane) & 1u) {
-                        const float2 v = lds_f2(a_col_me + istar * 8);
-                        rr = ma(v.x, v.y, e_me, e_star, nb);
+            if (__all_sync(FULL, r_pick < mtop)) {  // (a vote, so that the compiler sees a warp-uniform branch)
+                // ---- the common case (C3: 99.8 % of the hops): one of the 32 cached top events.
+                //      lane = the highest positive one whose interval starts below the threshold.
+                uint32_t bal = __ballot_sync(FULL, pre < r_pick) & posm;
+                if (!bal) bal = posm & (0u - posm);
+                if (!bal) {  // no transition possible (simulation.go:297 would divide by zero), or NaN
+                    dead = true;
+                    break;
+                }
+                const int istar = 31 - __clz(bal);
+                const int partner = (int)(__shfl_sync(FULL, (uint32_t)__double2loint(pre), istar) & 63u);
+                const bool rowocc = (occ >> istar) & 1u;
+                from = rowocc ? istar : partner;
+                to = rowocc ? partner : istar;
+            } else {
+                // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
+                if (!swept) sweep();
+                const double rres = r_pick - mtop;
+                const double incl = scan_d((double)rest);
+                double ex = __shfl_up_sync(FULL, incl, 1);
+                if (lane == 0) ex = 0.0;
+                const uint32_t rpos = __ballot_sync(FULL, rest > 0.0f);
+                uint32_t bal = __ballot_sync(FULL, ex < rres) & rpos;
+                if (!bal) bal = rpos & (0u - rpos);
+                int istar;
+                float rf;
+                int skip;
+                if (bal) {
+                    istar = 31 - __clz(bal);
+                    rf = __shfl_sync(FULL, (float)(rres - ex), istar);
+                    skip = (int)__shfl_sync(FULL, ptn, istar);
+                } else {  // no mass outside the top events (rounding): take the last top event instead
+                    if (!posm) {
+                        dead = true;
+                        break;
                     }
-                    const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
-                    if (nz) {
-                        const float s = scan_f<5>(rr);
-                        const uint32_t b2 = __ballot_sync(FULL, s >= rf) & nz;
-                        if (b2) to = __ffs(b2) - 1;
-                        else {
-                            lastA = 31 - __clz(nz);
-                            sA = __shfl_sync(FULL, s, 31);
+                    istar = 31 - __clz(posm);
+                    rf = BIGE;
+                    skip = -1;
+                }
+                const bool rowocc = (occ >> istar) & 1u;
+                const float e_star = lds_f(a_mir + istar * 4);
+                if (rowocc) {
+                    from = istar;
+                    to = -1;
+                    int lastA = -1;
+                    float sA = 0.0f;
+                    const uint32_t emp = ~occ & accm;
+                    if (emp) {  // acceptor targets: istar -> empty `lane`
+                        float rr = 0.0f;
+                        if (((emp >> lane) & 1u) && lane != skip) {
+                            const float2 v = lds_f2(a_col_me + istar * 8);
+                            rr = ma(v.x, v.y, e_me, e_star, nb);
+                        }
+                        const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+                        if (nz) {
+                            const float s = scan_f<5>(rr);
+                            const uint32_t b2 = __ballot_sync(FULL, s >= rf) & nz;
+                            if (b2) to = __ffs(b2) - 1;
+                            else {
+                                lastA = 31 - __clz(nz);
+                                sA = __shfl_sync(FULL, s, 31);
+                            }
                         }
                     }
-                }
-                if (to < 0) {  // electrode targets: istar -> electrode `lane`
+                    if (to < 0) {  // electrode targets: istar -> electrode `lane`
+                        float rr = 0.0f;
+                        if (lane < P && N + lane != skip)
+                            rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
+                        const int e = pick_group<5>(rr, rf - sA);
+                        to = (e >= 0) ? N + e : lastA;
+                    }
+                    if (to < 0 && skip < 0) to = (int)__shfl_sync(FULL, ptn, istar);  // rounding fallback: the top event
+                } else {  // empty acceptor: events electrode `lane` -> istar
+                    to = istar;
                     float rr = 0.0f;
-                    if (lane < P) rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
-                    const int e = pick_group<ESTEPS>(rr, rf - sA);
-                    to = (e >= 0) ? N + e : lastA;  // electrode group empty (rounding): last acceptor target
+                    if (lane < P && N + lane != skip)
+                        rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
+                    from = pick_group<5>(rr, rf);
+                    if (from >= 0) from += N;
+                    else if (skip < 0) from = (int)__shfl_sync(FULL, ptn, istar);
                 }
-            } else {  // empty acceptor: events electrode `lane` -> istar
-                to = istar;
-                float rr = 0.0f;
-                if (lane < P) rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
-                from = pick_group<ESTEPS>(rr, rf);
-                if (from >= 0) from += N;
-            }
-            if (to < 0 || from < 0) {
-                dead = true;
-                break;
+                if (to < 0 || from < 0) {
+                    dead = true;
+                    break;
+                }
             }
 
             // ---- tallies (simulation.go:309-317: pre-hop occupation, antisymmetric traffic)
@@ -394,26 +464,20 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 }
             }
 
-            // ---- apply the hop (simulation.go:107-130)
-            if (from < N) {
-                occ &= ~(1u << from);
-                eps64 -= (double)lds_f2(a_row_me + from * ROWB).y;
-            } else {
-                eoc -= (int)(lane == from - N);
-            }
-            if (to < N) {
-                occ |= (1u << to);
-                eps64 += (double)lds_f2(a_row_me + to * ROWB).y;
-            } else {
-                eoc += (int)(lane == to - N);
-            }
+            // ---- apply the hop (simulation.go:107-130); the energies follow from the new mask when next needed
+            if (from < N) occ &= ~(1u << from);
+            else eoc -= (int)(lane == from - N);
+            if (to < N) occ |= (1u << to);
+            else eoc += (int)(lane == to - N);
             if (K > 0) {  // prefetch the next state's cache line (lane 0 may have written it in this very hop)
                 __syncwarp();
                 slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
                 keyv = lds_u(a_keys + slot * 4);
                 pre = lds_d(a_cache + slot * G::ENTRY + lane * 8);
-                total = lds_d(a_cache + slot * G::ENTRY + 256);
-                rtot = lds_f(a_cache + slot * G::ENTRY + 264);
+                mtop = lds_d(a_cache + slot * G::ENTRY + 256);
+                total = lds_d(a_cache + slot * G::ENTRY + 264);
+                rtot = lds_f(a_cache + slot * G::ENTRY + 272);
+                posm = lds_u(a_cache + slot * G::ENTRY + 276);
             }
         }
         h = hend;
@@ -433,7 +497,7 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     if (lane < N) {
         if (E.occupation_out) E.occupation_out[m * N + lane] = (occ >> lane) & 1u;
         if (DBG && E.avg_occupation) E.avg_occupation[m * N + lane] = occtime;
-        if (E.site_energies_out) E.site_energies_out[m * S + lane] = eps64;
+        if (E.site_energies_out) E.site_energies_out[m * S + lane] = energy_of(occ);
     }
     if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)ve_mine;
     if (DBG && E.misses && lane == 0) E.misses[m] = n_miss;
