@@ -117,6 +117,12 @@ __device__ __forceinline__ double scan_d(double v) {
     return v;
 }
 
+// Broadcast of a small unsigned value from one lane through REDUX.OR: unlike SHFL the result is warp-uniform
+// for the compiler, so everything derived from it (the occupation mask, loop trip counts) stays uniform.
+__device__ __forceinline__ uint32_t bcast_u(uint32_t v, int src, int lane) {
+    return __reduce_or_sync(FULL, lane == src ? v : 0u);
+}
+
 // Miller-Abrahams factor in the reference's operation order (simulation.go:66-77): dE = e_to - e_from - kd,
 // rate = tc * exp(-dE/kT) for dE > 0, else tc.   nb = -log2(e)/kT.
 __device__ __forceinline__ float ma(float tc, float kd, float e_to, float e_from, float nb) {
@@ -133,6 +139,64 @@ __device__ __forceinline__ int pick_group(float rr, float thr) {
     const float s = scan_f<STEPS>(rr);
     const uint32_t bal = __ballot_sync(FULL, s >= thr) & nz;
     return bal ? (__ffs(bal) - 1) : (31 - __clz(nz));
+}
+
+// Site energy of acceptor `lane` for occupation mask o, from scratch: E_const - sum over EMPTY j of I0*R/d_ij
+// (simulation.go:226-234).  fp64 sums of fp32 terms in ascending j: exact, hence a pure function of the mask.
+__device__ __forceinline__ double energy_of(uint32_t o, uint32_t accm, double E64, uint32_t a_row_me) {
+    double e = E64;
+    uint32_t mm = ~o & accm;
+    while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        e -= (double)lds_f2(a_row_me + j * ROWB).y;
+    }
+    return e;
+}
+
+// Sweep: every allowed pair of the current state exactly once.  Per lane: its LARGEST rate (top, with the partner
+// site ptn) and the sum of all its other rates (rest).  Publishes the fp32 energies to the warp's mirror.
+template <int PT>
+__device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double E64, int lane, int N, int P, float nb,
+                                            const float (&ve_reg)[PT > 0 ? PT : 1], uint32_t a_row_me, uint32_t a_mir,
+                                            uint32_t a_elF, uint32_t a_elR, float &e_me, float &top, float &rest,
+                                            uint32_t &ptn) {
+    e_me = (float)energy_of(occ, accm, E64, a_row_me);
+    __syncwarp();
+    sts_f(a_mir + lane * 4, e_me);
+    __syncwarp();
+    const bool o = (occ >> lane) & 1u;
+    const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
+    const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
+    const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
+    top = 0.0f; rest = 0.0f; ptn = 0;
+    uint32_t mm = ~occ & accm;
+    while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const float ej = lds_f(a_mir + j * 4);
+        const float2 v = lds_f2(a_row_me + j * ROWB);
+        const float x = ma(v.x, v.y, ej, src, nb);
+        rest += fminf(x, top);
+        if (x > top) ptn = j;
+        top = fmaxf(x, top);
+    }
+    if (PT > 0) {
+#pragma unroll
+        for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
+            const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((ve_reg[e] - e_me) * nbs, 0.0f));
+            rest += fminf(x, top);
+            if (x > top) ptn = N + e;
+            top = fmaxf(x, top);
+        }
+    } else {
+        for (int e = 0; e < P; ++e) {
+            const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
+            rest += fminf(x, top);
+            if (x > top) ptn = N + e;
+            top = fmaxf(x, top);
+        }
+    }
 }
 
 template <int LOGK>
@@ -219,62 +283,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     bool dead = false;
     long long n_miss = 0;
 
-    // Site energies of the current state, from scratch: E_const - sum over EMPTY j of I0*R/d_ij (simulation.go:226-234).
-    // fp64 sums of fp32 terms in ascending j: exact, hence a pure function of the occupation mask.
-    auto energy_of = [&](uint32_t o) -> double {
-        double e = E64;
-        uint32_t mm = ~o & accm;
-        while (mm) {
-            const int j = __ffs(mm) - 1;
-            mm &= mm - 1;
-            e -= (double)lds_f2(a_row_me + j * ROWB).y;
-        }
-        return e;
-    };
-
-    // Sweep: every allowed pair of the current state exactly once.  Per lane: its LARGEST rate (top, with the
-    // partner site ptn), and the sum of all its other rates (rest).  Publishes the fp32 energies to the mirror.
     float e_me = 0.0f, top = 0.0f, rest = 0.0f;
     uint32_t ptn = 0;
-    auto sweep = [&]() {
-        if (DBG) ++n_miss;
-        e_me = (float)energy_of(occ);
-        __syncwarp();
-        sts_f(a_mir + lane * 4, e_me);
-        __syncwarp();
-        const bool o = (occ >> lane) & 1u;
-        const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
-        const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
-        const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
-        top = 0.0f; rest = 0.0f; ptn = 0;
-        uint32_t mm = ~occ & accm;
-        while (mm) {
-            const int j = __ffs(mm) - 1;
-            mm &= mm - 1;
-            const float ej = lds_f(a_mir + j * 4);
-            const float2 v = lds_f2(a_row_me + j * ROWB);
-            const float x = ma(v.x, v.y, ej, src, nb);
-            rest += fminf(x, top);
-            if (x > top) ptn = j;
-            top = fmaxf(x, top);
-        }
-        if (PT > 0) {
-#pragma unroll
-            for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
-                const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((ve_reg[e] - e_me) * nbs, 0.0f));
-                rest += fminf(x, top);
-                if (x > top) ptn = N + e;
-                top = fmaxf(x, top);
-            }
-        } else {
-            for (int e = 0; e < P; ++e) {
-                const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
-                rest += fminf(x, top);
-                if (x > top) ptn = N + e;
-                top = fmaxf(x, top);
-            }
-        }
-    };
 
     uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
     // Loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied:
@@ -317,7 +327,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             if (K > 0) hit = __all_sync(FULL, keyv == occ);
             bool swept = false;
             if (!hit) {
-                sweep();
+                if (DBG) ++n_miss;
+                sweep_state<PT>(occ, accm, E64, lane, N, P, nb, ve_reg, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
                 swept = true;
                 const double incl = scan_d((double)top);
                 mtop = __shfl_sync(FULL, incl, 31);
@@ -362,20 +373,26 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             if (__all_sync(FULL, r_pick < mtop)) {  // (a vote, so that the compiler sees a warp-uniform branch)
                 // ---- the common case (C3: 99.8 % of the hops): one of the 32 cached top events.
                 //      lane = the highest positive one whose interval starts below the threshold.
-                uint32_t bal = __ballot_sync(FULL, pre < r_pick) & posm;
-                if (!bal) bal = posm & (0u - posm);
+                // posm was loaded from shared memory; a vote makes its warp-uniformity visible to the compiler
+                const uint32_t posu = __ballot_sync(FULL, (posm >> lane) & 1u);
+                uint32_t bal = __ballot_sync(FULL, pre < r_pick) & posu;
+                if (!bal) bal = posu & (0u - posu);
+                // (every loop exit is decided by a vote: the compiler must be able to see that the warp stays converged)
                 if (!bal) {  // no transition possible (simulation.go:297 would divide by zero), or NaN
                     dead = true;
                     break;
                 }
                 const int istar = 31 - __clz(bal);
-                const int partner = (int)(__shfl_sync(FULL, (uint32_t)__double2loint(pre), istar) & 63u);
+                const int partner = (int)bcast_u((uint32_t)__double2loint(pre) & 63u, istar, lane);
                 const bool rowocc = (occ >> istar) & 1u;
                 from = rowocc ? istar : partner;
                 to = rowocc ? partner : istar;
             } else {
                 // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
-                if (!swept) sweep();
+                if (!swept) {
+                    if (DBG) ++n_miss;
+                    sweep_state<PT>(occ, accm, E64, lane, N, P, nb, ve_reg, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                }
                 const double rres = r_pick - mtop;
                 const double incl = scan_d((double)rest);
                 double ex = __shfl_up_sync(FULL, incl, 1);
@@ -386,20 +403,21 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                 int istar;
                 float rf;
                 int skip;
-                if (bal) {
+                if (__any_sync(FULL, bal != 0u)) {
                     istar = 31 - __clz(bal);
                     rf = __shfl_sync(FULL, (float)(rres - ex), istar);
-                    skip = (int)__shfl_sync(FULL, ptn, istar);
+                    skip = (int)bcast_u(ptn, istar, lane);
                 } else {  // no mass outside the top events (rounding): take the last top event instead
-                    if (!posm) {
+                    const uint32_t posu = __ballot_sync(FULL, (posm >> lane) & 1u);
+                    if (!posu) {
                         dead = true;
                         break;
                     }
-                    istar = 31 - __clz(posm);
+                    istar = 31 - __clz(posu);
                     rf = BIGE;
                     skip = -1;
                 }
-                const bool rowocc = (occ >> istar) & 1u;
+                const bool rowocc = __any_sync(FULL, (occ >> istar) & 1u);
                 const float e_star = lds_f(a_mir + istar * 4);
                 if (rowocc) {
                     from = istar;
@@ -431,7 +449,7 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                         const int e = pick_group<5>(rr, rf - sA);
                         to = (e >= 0) ? N + e : lastA;
                     }
-                    if (to < 0 && skip < 0) to = (int)__shfl_sync(FULL, ptn, istar);  // rounding fallback: the top event
+                    if (to < 0 && skip < 0) to = (int)bcast_u(ptn, istar, lane);  // rounding fallback: the top event
                 } else {  // empty acceptor: events electrode `lane` -> istar
                     to = istar;
                     float rr = 0.0f;
@@ -439,9 +457,9 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
                         rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
                     from = pick_group<5>(rr, rf);
                     if (from >= 0) from += N;
-                    else if (skip < 0) from = (int)__shfl_sync(FULL, ptn, istar);
+                    else if (skip < 0) from = (int)bcast_u(ptn, istar, lane);
                 }
-                if (to < 0 || from < 0) {
+                if (__any_sync(FULL, to < 0 || from < 0)) {
                     dead = true;
                     break;
                 }
@@ -497,7 +515,7 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     if (lane < N) {
         if (E.occupation_out) E.occupation_out[m * N + lane] = (occ >> lane) & 1u;
         if (DBG && E.avg_occupation) E.avg_occupation[m * N + lane] = occtime;
-        if (E.site_energies_out) E.site_energies_out[m * S + lane] = energy_of(occ);
+        if (E.site_energies_out) E.site_energies_out[m * S + lane] = energy_of(occ, accm, E64, a_row_me);
     }
     if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)ve_mine;
     if (DBG && E.misses && lane == 0) E.misses[m] = n_miss;
