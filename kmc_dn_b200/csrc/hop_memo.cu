@@ -45,6 +45,7 @@ namespace kmcb200 {
 #define BIGE 1.0e30f
 #define ROWB 264u  // bytes per acceptor-target row of the pair table: 33 float2
 #define ELB 132u   // bytes per electrode row of the electrode planes: 33 float
+#define GENTRY 288u  // bytes per entry of the second-level (global) cache
 
 __device__ __forceinline__ float lds_f(uint32_t a) {
     float v;
@@ -208,13 +209,15 @@ struct MemoGeom {
 };
 
 template <int PT, int LOGK, bool DBG>
-__global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
+__global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = MemoGeom<LOGK>;
     constexpr int K = G::K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = L.N, S = L.S;
     const int P = PT > 0 ? PT : L.P;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
+    // broadcast from lane 0, so that the compiler knows the warp index is warp-uniform (it drives the member loop)
+    const int warp = __shfl_sync(FULL, tid >> 5, 0);
 
     // ---- stage the layout: pair table for acceptor targets, two planes (i->e, e->i) for the electrodes
     {
@@ -230,9 +233,6 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     }
     __syncthreads();
 
-    const int64_t m = (int64_t)blockIdx.x * nwarps + warp;
-    if (m >= E.B) return;
-
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
@@ -243,6 +243,15 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     const uint32_t a_elR_e = a_elR + lane * ELB;      // + istar*4    : electrode lane -> istar
     const uint32_t accm = (N >= 32) ? ~0u : ((1u << N) - 1u);
 
+    // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of GENTRY bytes,
+    // {32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | u32 posm | u32 key | pad}.  Direct-mapped with
+    // an independent hash; looked up on a first-level miss, filled together with the first level.
+    const int GLOG = (K > 0) ? E.gtab_log : 0;
+    const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
+    unsigned char *gtab = (GLOG > 0) ? E.gtab + ((size_t)wslot << GLOG) * GENTRY : nullptr;
+
+    // ---- persistent: this warp slot runs members wslot, wslot + #slots, ...
+    for (int64_t m = wslot; m < E.B; m += (int64_t)gridDim.x * nwarps) {
     // ---- member parameters
     const float nb = -1.4426950408889634f / (float)E.kT[m];
     const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;  // electrode `lane`
@@ -253,8 +262,11 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
 #pragma unroll
         for (int e = 0; e < (PT > 0 ? PT : 1); ++e) ve_reg[e] = lds_f(a_mir + 128 + e * 4);
     }
-    if (K > 0) {  // empty cache: a key that hashes to another slot can never hit
+    if (K > 0) {  // empty caches: a key that hashes to another slot can never hit
         if (lane < K) sts_u(a_keys + lane * 4, lane == 0 ? 1u : 0u);
+        if (GLOG > 0)
+            for (int e = lane; e < (1 << GLOG); e += 32)
+                __stcg(reinterpret_cast<unsigned int *>(gtab + (size_t)e * GENTRY + 280), e == 0 ? 1u : 0u);
     }
 
     // ---- initial state
@@ -327,21 +339,48 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
             if (K > 0) hit = __all_sync(FULL, keyv == occ);
             bool swept = false;
             if (!hit) {
-                if (DBG) ++n_miss;
-                sweep_state<PT>(occ, accm, E64, lane, N, P, nb, ve_reg, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
-                swept = true;
-                const double incl = scan_d((double)top);
-                mtop = __shfl_sync(FULL, incl, 31);
-                double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
-                if (lane == 0) ex = 0.0;
-                double rsum = (double)rest;
+                bool hit2 = false;
+                unsigned char *gent = nullptr;
+                if (GLOG > 0) {  // second level (global memory, L2): all loads in flight at once, one latency
+                    gent = gtab + (size_t)((occ * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * GENTRY;
+                    const double g_pre = __ldcg(reinterpret_cast<const double *>(gent + lane * 8));
+                    const uint4 g0 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // mtop | total
+                    const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 272));  // rtot | posm | key | pad
+                    hit2 = __all_sync(FULL, g1.z == occ);
+                    if (hit2) {
+                        pre = g_pre;
+                        mtop = __hiloint2double((int)g0.y, (int)g0.x);
+                        total = __hiloint2double((int)g0.w, (int)g0.z);
+                        rtot = __uint_as_float(g1.x);
+                        posm = g1.y;
+                    }
+                }
+                if (!hit2) {
+                    if (DBG) ++n_miss;
+                    sweep_state<PT>(occ, accm, E64, lane, N, P, nb, ve_reg, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                    swept = true;
+                    const double incl = scan_d((double)top);
+                    mtop = __shfl_sync(FULL, incl, 31);
+                    double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
+                    if (lane == 0) ex = 0.0;
+                    double rsum = (double)rest;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
-                total = mtop + rsum;
-                rtot = rcp_approx((float)total);
-                posm = __ballot_sync(FULL, top > 0.0f);
-                pre = __hiloint2double(__double2hiint(ex), (__double2loint(ex) & ~63) | (int)ptn);
-                if (K > 0) {
+                    for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
+                    total = mtop + rsum;
+                    rtot = rcp_approx((float)total);
+                    posm = __ballot_sync(FULL, top > 0.0f);
+                    pre = __hiloint2double(__double2hiint(ex), (__double2loint(ex) & ~63) | (int)ptn);
+                    if (GLOG > 0) {
+                        __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
+                        if (lane == 0) {
+                            __stcg(reinterpret_cast<uint4 *>(gent + 256),
+                                   make_uint4((uint32_t)__double2loint(mtop), (uint32_t)__double2hiint(mtop),
+                                              (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
+                            __stcg(reinterpret_cast<uint4 *>(gent + 272), make_uint4(__float_as_uint(rtot), posm, occ, 0u));
+                        }
+                    }
+                }
+                if (K > 0) {  // install in the first level
                     sts_d(a_cache + slot * G::ENTRY + lane * 8, pre);
                     if (lane == 0) {
                         sts_d(a_cache + slot * G::ENTRY + 256, mtop);
@@ -519,6 +558,8 @@ __global__ void __launch_bounds__(256) kmc_memo_kernel(const LayoutDev L, const 
     }
     if (E.site_energies_out && lane < P) E.site_energies_out[m * S + N + lane] = (double)ve_mine;
     if (DBG && E.misses && lane == 0) E.misses[m] = n_miss;
+    __syncwarp();
+    }  // members of this warp slot
 }
 
 // ---- parity probe: energies + dense rate matrix of one state with the production arithmetic
@@ -558,38 +599,55 @@ __global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, co
 }
 
 template <int PT, int LOGK>
-static cudaError_t launch_memo_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches) {
+static cudaError_t launch_memo_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     using G = MemoGeom<LOGK>;
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e || E.misses;
     int warps = 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
-    const unsigned grid = (unsigned)((E.B + warps - 1) / warps);
     auto kern = dbg ? kmc_memo_kernel<PT, LOGK, true> : kmc_memo_kernel<PT, LOGK, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+    // persistent CTAs: as many as stay resident; every warp slot loops over its members
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+    if (err != cudaSuccess) return err;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t want = (E.B + warps - 1) / warps;
+    const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
+    if (plan_only) {
+        plan_only->warp_slots = (int64_t)grid * warps;
+        return cudaSuccess;
+    }
     kern<<<grid, warps * 32, smem, st>>>(L, E);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
 
 template <int PT>
-static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches) {
+static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
     switch (logk) {
-        case -1: return launch_memo_t<PT, -1>(L, E, st, launches);
-        case 3: return launch_memo_t<PT, 3>(L, E, st, launches);
-        case 5: return launch_memo_t<PT, 5>(L, E, st, launches);
-        default: return launch_memo_t<PT, 4>(L, E, st, launches);
+        case -1: return launch_memo_t<PT, -1>(L, E, st, launches, plan);
+        case 3: return launch_memo_t<PT, 3>(L, E, st, launches, plan);
+        case 5: return launch_memo_t<PT, 5>(L, E, st, launches, plan);
+        default: return launch_memo_t<PT, 4>(L, E, st, launches, plan);
     }
 }
 
-// logk: log2(cache slots per warp); -1 disables the memoisation (same code path, every hop a miss)
-cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches) {
-    if (E.B <= 0) return cudaSuccess;
+// logk: log2(first-level cache slots per warp); -1 disables the memoisation (same code path, every hop a miss).
+// plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the
+// second-level table E.gtab = warp_slots * 2^E.gtab_log * 288 bytes from it.
+cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
+    if (E.B <= 0) {
+        if (plan) plan->warp_slots = 0;
+        return cudaSuccess;
+    }
     if (L.N > 32 || L.P > 32 || L.pitchf != 33) return cudaErrorInvalidValue;
-    if (L.P == 8) return launch_memo_p<8>(L, E, logk, st, launches);
-    if (L.P == 2) return launch_memo_p<2>(L, E, logk, st, launches);
-    return launch_memo_p<0>(L, E, logk, st, launches);
+    if (L.P == 8) return launch_memo_p<8>(L, E, logk, st, launches, plan);
+    if (L.P == 2) return launch_memo_p<2>(L, E, logk, st, launches, plan);
+    return launch_memo_p<0>(L, E, logk, st, launches, plan);
 }
 
 cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const double *electrode_v, double kT,

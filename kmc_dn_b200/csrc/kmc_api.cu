@@ -44,6 +44,9 @@ struct kmcb200_layout {
     // grow-only device workspace for host-pointer calls
     void *ws = nullptr;
     size_t ws_bytes = 0;
+    // second-level state cache of the memoised kernel (warp_slots x 2^glog x 288 B), grow-only
+    void *gtab = nullptr;
+    size_t gtab_bytes = 0;
     std::mutex mu;
 };
 
@@ -161,6 +164,7 @@ extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     cudaFree(lay->dev.tbl); cudaFree(lay->dev.tblf); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
     cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
     cudaFree(lay->ws);
+    cudaFree(lay->gtab);
     delete lay;
 }
 
@@ -295,9 +299,24 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     else if (exact) le = launch_exact(D, E, st, &launches);
     else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
     else if (D.N <= 32 && !getenv("KMCB200_NO_MEMO_KERNEL")) {
-        int logk = 4;
+        int logk = 4, glog = 8;
         if (const char *ev = getenv("KMCB200_MEMO_LOGK")) logk = atoi(ev);
+        if (const char *ev = getenv("KMCB200_GTAB_LOG")) glog = atoi(ev);
         if (a->flags & KMCB200_FLAG_NO_MEMO) logk = -1;
+        if (logk < 0 || glog < 1 || glog > 12) glog = 0;
+        E.gtab = nullptr; E.gtab_log = 0;
+        if (glog > 0) {  // second-level cache table: one region per persistent warp slot, kept with the layout
+            MemoPlan plan{0};
+            le = launch_memo(D, E, logk, st, nullptr, &plan);
+            if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
+            const size_t bytes = ((size_t)plan.warp_slots << glog) * 288;
+            if (bytes > lay->gtab_bytes) {
+                if (lay->gtab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->gtab)); lay->gtab = nullptr; lay->gtab_bytes = 0; }
+                CU(cudaMalloc(&lay->gtab, bytes));
+                lay->gtab_bytes = bytes;
+            }
+            E.gtab = (unsigned char *)lay->gtab; E.gtab_log = glog;
+        }
         le = launch_memo(D, E, logk, st, &launches);
     } else le = launch_fast(D, E, st, &launches);
     g_launches += launches;

@@ -40,11 +40,15 @@ struct EnsembleDev {
     long long *misses;  // [B] rate-structure evaluations (cache misses) per member, or null
     double *prob_occupation, *prob_electrode_occ;  // MODE_PROB: fractional occupations [B,N], electrode tallies [B,P]
     double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
+    unsigned char *gtab;  // memoised kernel: second-level cache, warp_slots * 2^gtab_log entries of 288 B (or null)
+    int gtab_log;         // log2(entries per warp slot); 0 = no second level
 };
 
 // launchers (return cudaError_t of the launch)
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
-cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches);
+struct MemoPlan { int64_t warp_slots; };
+cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
+                        MemoPlan *plan_only = nullptr);
 cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_prob(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
