@@ -250,8 +250,13 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
     unsigned char *gtab = (GLOG > 0) ? E.gtab + ((size_t)wslot << GLOG) * GENTRY : nullptr;
 
-    // ---- persistent: this warp slot runs members wslot, wslot + #slots, ...
-    for (int64_t m = wslot; m < E.B; m += (int64_t)gridDim.x * nwarps) {
+    // ---- persistent: every warp slot pulls members from a global queue until it is empty (members differ in cost --
+    //      the miss rate depends on the voltages -- so a static split would leave slots idle at the end)
+    for (;;) {
+        unsigned long long mq = 0;
+        if (lane == 0) mq = atomicAdd(E.queue, 1ULL);
+        const int64_t m = (int64_t)__shfl_sync(FULL, mq, 0);
+        if (m >= E.B) break;
     // ---- member parameters
     const float nb = -1.4426950408889634f / (float)E.kT[m];
     const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;  // electrode `lane`

@@ -47,6 +47,7 @@ struct kmcb200_layout {
     // second-level state cache of the memoised kernel (warp_slots x 2^glog x 288 B), grow-only
     void *gtab = nullptr;
     size_t gtab_bytes = 0;
+    unsigned long long *queue = nullptr;  // member work queue of the persistent kernel
     std::mutex mu;
 };
 
@@ -165,6 +166,7 @@ extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
     cudaFree(lay->ws);
     cudaFree(lay->gtab);
+    cudaFree(lay->queue);
     delete lay;
 }
 
@@ -317,6 +319,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             }
             E.gtab = (unsigned char *)lay->gtab; E.gtab_log = glog;
         }
+        if (!lay->queue) CU(cudaMalloc((void **)&lay->queue, 256));
+        CU(cudaMemsetAsync(lay->queue, 0, 256, st));
+        E.queue = lay->queue;
         le = launch_memo(D, E, logk, st, &launches);
     } else le = launch_fast(D, E, st, &launches);
     g_launches += launches;
