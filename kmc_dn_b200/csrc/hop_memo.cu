@@ -23,8 +23,8 @@
 // energies are exact.  Every warp keeps a direct-mapped cache in shared memory:
 //
 //     key   = 32-bit occupation mask              (slot = multiplicative hash, 2^LOGK slots)
-//     value = the fp64 exclusive prefix over the 32 lane sums (one double per lane, lane-private column),
-//             the fp64 total and its fp32 reciprocal (272 B per state)
+//     value = per lane its LARGEST rate as an fp64 exclusive prefix over the lanes (with the partner site in the
+//             6 mantissa LSBs), the mass of these top events, the fp64 total and its fp32 reciprocal (288 B)
 //
 // Hit:  the sweep and the fp64 scan are skipped; the hop costs the lookup, the first-level ballot, the
 //       second-level re-evaluation of ONE lane's targets and the state update.
@@ -200,17 +200,18 @@ __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double 
     }
 }
 
-template <int LOGK>
+template <int LOGK, int PT>
 struct MemoGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
-    static constexpr int KEYB = K > 4 ? K * 4 : 16;
-    static constexpr int ENTRY = 280;  // 32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | u32 posm
-    static constexpr int WARP_BYTES = 256 + 1024 + KEYB + K * ENTRY;  // mirror | variates | keys | entries
+    static constexpr int ENTRY = 288;  // 32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | pad | u32 key | pad
+    // mirror (acceptor energies 128 B + electrode energies) | variates 64 x 16 B | entries
+    static constexpr int MIRB = PT > 0 ? 128 + ((PT * 4 + 15) & ~15) : 256;
+    static constexpr int WARP_BYTES = MIRB + 1024 + K * ENTRY;
 };
 
 template <int PT, int LOGK, bool DBG>
 __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
-    using G = MemoGeom<LOGK>;
+    using G = MemoGeom<LOGK, PT>;
     constexpr int K = G::K;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = L.N, S = L.S;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
-    const uint32_t a_mir = wb, a_rng = wb + 256, a_keys = wb + 1280, a_cache = wb + 1280 + G::KEYB;
+    const uint32_t a_mir = wb, a_rng = wb + G::MIRB, a_cache = wb + G::MIRB + 1024;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t accm = (N >= 32) ? ~0u : ((1u << N) - 1u);
 
     // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of GENTRY bytes,
-    // {32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | u32 posm | u32 key | pad}.  Direct-mapped with
+    // {32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | pad | u32 key | pad}.  Direct-mapped with
     // an independent hash; looked up on a first-level miss, filled together with the first level.
     const int GLOG = (K > 0) ? E.gtab_log : 0;
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
         for (int e = 0; e < (PT > 0 ? PT : 1); ++e) ve_reg[e] = lds_f(a_mir + 128 + e * 4);
     }
     if (K > 0) {  // empty caches: a key that hashes to another slot can never hit
-        if (lane < K) sts_u(a_keys + lane * 4, lane == 0 ? 1u : 0u);
+        if (lane < K) sts_u(a_cache + lane * G::ENTRY + 280, lane == 0 ? 1u : 0u);
         if (GLOG > 0)
             for (int e = lane; e < (1 << GLOG); e += 32)
                 __stcg(reinterpret_cast<unsigned int *>(gtab + (size_t)e * GENTRY + 280), e == 0 ? 1u : 0u);
@@ -307,11 +308,10 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     // Loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied:
     //   pre   exclusive fp64 prefix over the lanes' TOP rates; its 6 mantissa LSBs carry the lane's partner site
     //   mtop  total mass of the top events; total = mtop + mass of all other events; rtot = 1/total (fp32)
-    //   posm  lanes whose top rate is positive
+    //         (+inf for a lane without a positive rate: it can never win the ballot)
     uint32_t keyv = ~occ;  // first hop: miss
     double pre = 0.0, mtop = 0.0, total = 0.0;
     float rtot = 0.0f;
-    uint32_t posm = 0;
     __syncwarp();
 
     int64_t h = 0;
@@ -350,14 +350,13 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     gent = gtab + (size_t)((occ * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * GENTRY;
                     const double g_pre = __ldcg(reinterpret_cast<const double *>(gent + lane * 8));
                     const uint4 g0 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // mtop | total
-                    const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 272));  // rtot | posm | key | pad
+                    const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 272));  // rtot | pad | key | pad
                     hit2 = __all_sync(FULL, g1.z == occ);
                     if (hit2) {
                         pre = g_pre;
                         mtop = __hiloint2double((int)g0.y, (int)g0.x);
                         total = __hiloint2double((int)g0.w, (int)g0.z);
                         rtot = __uint_as_float(g1.x);
-                        posm = g1.y;
                     }
                 }
                 if (!hit2) {
@@ -373,15 +372,15 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
                     total = mtop + rsum;
                     rtot = rcp_approx((float)total);
-                    posm = __ballot_sync(FULL, top > 0.0f);
-                    pre = __hiloint2double(__double2hiint(ex), (__double2loint(ex) & ~63) | (int)ptn);
+                    pre = (top > 0.0f) ? __hiloint2double(__double2hiint(ex), (__double2loint(ex) & ~63) | (int)ptn)
+                                       : __longlong_as_double(0x7ff0000000000000LL);
                     if (GLOG > 0) {
                         __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
                         if (lane == 0) {
                             __stcg(reinterpret_cast<uint4 *>(gent + 256),
                                    make_uint4((uint32_t)__double2loint(mtop), (uint32_t)__double2hiint(mtop),
                                               (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
-                            __stcg(reinterpret_cast<uint4 *>(gent + 272), make_uint4(__float_as_uint(rtot), posm, occ, 0u));
+                            __stcg(reinterpret_cast<uint4 *>(gent + 272), make_uint4(__float_as_uint(rtot), 0u, occ, 0u));
                         }
                     }
                 }
@@ -391,8 +390,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                         sts_d(a_cache + slot * G::ENTRY + 256, mtop);
                         sts_d(a_cache + slot * G::ENTRY + 264, total);
                         sts_f(a_cache + slot * G::ENTRY + 272, rtot);
-                        sts_u(a_cache + slot * G::ENTRY + 276, posm);
-                        sts_u(a_keys + slot * 4, occ);
+                        sts_u(a_cache + slot * G::ENTRY + 280, occ);
                     }
                 }
             }
@@ -413,14 +411,13 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                 t_acc += dtd;
             }
 
-            int from, to;
+            int from = 0, to = 0;
+            uint32_t occ_new = occ;
+            int deo = 0;  // this lane's electrode tally change
             if (__all_sync(FULL, r_pick < mtop)) {  // (a vote, so that the compiler sees a warp-uniform branch)
                 // ---- the common case (C3: 99.8 % of the hops): one of the 32 cached top events.
                 //      lane = the highest positive one whose interval starts below the threshold.
-                // posm was loaded from shared memory; a vote makes its warp-uniformity visible to the compiler
-                const uint32_t posu = __ballot_sync(FULL, (posm >> lane) & 1u);
-                uint32_t bal = __ballot_sync(FULL, pre < r_pick) & posu;
-                if (!bal) bal = posu & (0u - posu);
+                const uint32_t bal = __ballot_sync(FULL, pre < r_pick);
                 // (every loop exit is decided by a vote: the compiler must be able to see that the warp stays converged)
                 if (!bal) {  // no transition possible (simulation.go:297 would divide by zero), or NaN
                     dead = true;
@@ -428,9 +425,17 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                 }
                 const int istar = 31 - __clz(bal);
                 const int partner = (int)bcast_u((uint32_t)__double2loint(pre) & 63u, istar, lane);
-                const bool rowocc = (occ >> istar) & 1u;
-                from = rowocc ? istar : partner;
-                to = rowocc ? partner : istar;
+                // apply the hop (simulation.go:107-130): lane istar's site flips; the partner is an acceptor or an electrode
+                if ((occ >> istar) & 1u) {  // istar -> partner
+                    occ_new = occ & ~(1u << istar);
+                    if (partner < N) occ_new |= 1u << partner;
+                    else deo = (int)(lane == partner - N);
+                    if (DBG) { from = istar; to = partner; }
+                } else {                    // electrode partner -> istar
+                    occ_new = occ | (1u << istar);
+                    deo = -(int)(lane == partner - N);
+                    if (DBG) { from = partner; to = istar; }
+                }
             } else {
                 // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
                 if (!swept) {
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     rf = __shfl_sync(FULL, (float)(rres - ex), istar);
                     skip = (int)bcast_u(ptn, istar, lane);
                 } else {  // no mass outside the top events (rounding): take the last top event instead
-                    const uint32_t posu = __ballot_sync(FULL, (posm >> lane) & 1u);
+                    const uint32_t posu = __ballot_sync(FULL, pre < __longlong_as_double(0x7ff0000000000000LL));
                     if (!posu) {
                         dead = true;
                         break;
@@ -507,6 +512,10 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     dead = true;
                     break;
                 }
+                if (from < N) occ_new &= ~(1u << from);
+                else deo -= (int)(lane == from - N);
+                if (to < N) occ_new |= (1u << to);
+                else deo += (int)(lane == to - N);
             }
 
             // ---- tallies (simulation.go:309-317: pre-hop occupation, antisymmetric traffic)
@@ -526,20 +535,19 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                 }
             }
 
-            // ---- apply the hop (simulation.go:107-130); the energies follow from the new mask when next needed
-            if (from < N) occ &= ~(1u << from);
-            else eoc -= (int)(lane == from - N);
-            if (to < N) occ |= (1u << to);
-            else eoc += (int)(lane == to - N);
+            // ---- the new state; the energies follow from the new mask when next needed
+            occ = occ_new;
+            eoc += deo;
             if (K > 0) {  // prefetch the next state's cache line (lane 0 may have written it in this very hop)
                 __syncwarp();
                 slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-                keyv = lds_u(a_keys + slot * 4);
                 pre = lds_d(a_cache + slot * G::ENTRY + lane * 8);
-                mtop = lds_d(a_cache + slot * G::ENTRY + 256);
-                total = lds_d(a_cache + slot * G::ENTRY + 264);
-                rtot = lds_f(a_cache + slot * G::ENTRY + 272);
-                posm = lds_u(a_cache + slot * G::ENTRY + 276);
+                const uint4 t0 = lds_u4(a_cache + slot * G::ENTRY + 256);  // mtop | total
+                const uint4 t1 = lds_u4(a_cache + slot * G::ENTRY + 272);  // rtot | pad | key | pad
+                mtop = __hiloint2double((int)t0.y, (int)t0.x);
+                total = __hiloint2double((int)t0.w, (int)t0.z);
+                rtot = __uint_as_float(t1.x);
+                keyv = t1.z;
             }
         }
         h = hend;
@@ -605,7 +613,7 @@ __global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, co
 
 template <int PT, int LOGK>
 static cudaError_t launch_memo_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
-    using G = MemoGeom<LOGK>;
+    using G = MemoGeom<LOGK, PT>;
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e || E.misses;
     int warps = 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
