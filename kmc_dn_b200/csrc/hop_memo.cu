@@ -23,16 +23,18 @@
 // energies are exact.  Every warp keeps a direct-mapped cache in shared memory:
 //
 //     key   = 32-bit occupation mask              (slot = multiplicative hash, 2^LOGK slots)
-//     value = per lane its LARGEST rate as an fp64 exclusive prefix over the lanes (with the partner site in the
-//             6 mantissa LSBs), the mass of these top events, the fp64 total and its fp32 reciprocal (288 B)
+//     value = per lane its LARGEST rate as a NORMALISED fp64 exclusive prefix over the lanes (with the event -- the
+//             partner site and the direction -- in the 7 mantissa LSBs), lane 31 = the normalised mass of these top
+//             events (sentinel), the fp32 reciprocal of the total rate and the fp64 total (272 B)
 //
-// Hit:  the sweep and the fp64 scan are skipped; the hop costs the lookup, the first-level ballot, the
-//       second-level re-evaluation of ONE lane's targets and the state update.
+// Hit:  the sweep and the fp64 scan are skipped; the hop costs the lookup, ONE ballot of prefix < uniform (the
+//       sentinel lane routes the 0.2 % of the hops that fall outside the top events to the exact slow path), one
+//       shuffle for the winning lane's event code and a branch-free update of the mask and the electrode tallies.
 // Miss: sweep + scan, then the prefix is parked in the slot.
 // Memoising a pure function cannot change a result: with the cache disabled (LOGK = -1 instantiation,
 // KMCB200_FLAG_NO_MEMO) the kernel produces bit-identical trajectories (tests/test_gpu_parity.py).
 // The reference's cache stores the full per-pair list per state (up to 150e6 floats per trajectory); here the
-// second level is recomputed instead of stored, so 272 B per state keep 16 states per warp on chip.
+// rest of the list is recomputed when needed instead of stored, so 272 B per state keep 16 states per warp on chip.
 //
 // Shared-memory accesses in the hop loop go through explicit ld/st.shared on 32-bit shared addresses: every
 // branch condition is then provably warp-uniform for the compiler (votes), and no generic-address arithmetic
@@ -45,7 +47,7 @@ namespace kmcb200 {
 #define BIGE 1.0e30f
 #define ROWB 264u  // bytes per acceptor-target row of the pair table: 33 float2
 #define ELB 132u   // bytes per electrode row of the electrode planes: 33 float
-#define GENTRY 288u  // bytes per entry of the second-level (global) cache
+#define ENTB 272u  // bytes per cache entry (both levels): 32 x f64 prefix | f32 1/total | u32 key | f64 total
 
 __device__ __forceinline__ float lds_f(uint32_t a) {
     float v;
@@ -159,7 +161,7 @@ __device__ __forceinline__ double energy_of(uint32_t o, uint32_t accm, double E6
 // site ptn) and the sum of all its other rates (rest).  Publishes the fp32 energies to the warp's mirror.
 template <int PT>
 __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double E64, int lane, int N, int P, float nb,
-                                            const float (&ve_reg)[PT > 0 ? PT : 1], uint32_t a_row_me, uint32_t a_mir,
+                                            uint32_t a_row_me, uint32_t a_mir,
                                             uint32_t a_elF, uint32_t a_elR, float &e_me, float &top, float &rest,
                                             uint32_t &ptn) {
     e_me = (float)energy_of(occ, accm, E64, a_row_me);
@@ -185,7 +187,7 @@ __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double 
     if (PT > 0) {
 #pragma unroll
         for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
-            const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((ve_reg[e] - e_me) * nbs, 0.0f));
+            const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
             rest += fminf(x, top);
             if (x > top) ptn = N + e;
             top = fmaxf(x, top);
@@ -203,11 +205,25 @@ __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double 
 template <int LOGK, int PT>
 struct MemoGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
-    static constexpr int ENTRY = 288;  // 32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | pad | u32 key | pad
+    static constexpr int ENTRY = (int)ENTB;
     // mirror (acceptor energies 128 B + electrode energies) | variates 64 x 16 B | entries
     static constexpr int MIRB = PT > 0 ? 128 + ((PT * 4 + 15) & ~15) : 256;
-    static constexpr int WARP_BYTES = MIRB + 1024 + K * ENTRY;
+    static constexpr int WARP_BYTES = MIRB + 1024 + (K > 0 ? K : 1) * ENTRY;  // K = 0: one scratch entry
 };
+
+// highest set bit (bfind: one FLO, no 31-clz round trip); shift that clamps (shl.b32 gives 0 for amounts > 31)
+__device__ __forceinline__ int bfind_u(uint32_t v) {
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+// single-bit mask 1 << n, 0 for n > 31 (BMSK: no constant operand to materialise)
+__device__ __forceinline__ uint32_t bit_clamp(uint32_t n) {
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(r) : "r"(n));
+    return r;
+}
+__device__ __forceinline__ void sts_u2(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y)); }
 
 template <int PT, int LOGK, bool DBG>
 __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
@@ -238,18 +254,20 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
     const uint32_t a_mir = wb, a_rng = wb + G::MIRB, a_cache = wb + G::MIRB + 1024;
+    const uint32_t a_cache_lane = a_cache + lane * 8u, a_cache_tail = a_cache + 256u;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
     const uint32_t a_elR_e = a_elR + lane * ELB;      // + istar*4    : electrode lane -> istar
-    const uint32_t accm = (N >= 32) ? ~0u : ((1u << N) - 1u);
+    const uint32_t accm = (1u << N) - 1u;             // N <= 31: lane 31 is never an acceptor (it holds the sentinel)
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
-    // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of GENTRY bytes,
-    // {32 x f64 prefix(+partner) | f64 mtop | f64 total | f32 1/total | pad | u32 key | pad}.  Direct-mapped with
-    // an independent hash; looked up on a first-level miss, filled together with the first level.
+    // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of ENTB bytes, same
+    // layout as the first level.  Direct-mapped with an independent hash; looked up on a first-level miss,
+    // filled together with the first level.
     const int GLOG = (K > 0) ? E.gtab_log : 0;
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
-    unsigned char *gtab = (GLOG > 0) ? E.gtab + ((size_t)wslot << GLOG) * GENTRY : nullptr;
+    unsigned char *gtab = (GLOG > 0) ? E.gtab + ((size_t)wslot << GLOG) * ENTB : nullptr;
 
     // ---- persistent: every warp slot pulls members from a global queue until it is empty (members differ in cost --
     //      the miss rate depends on the voltages -- so a static split would leave slots idle at the end)
@@ -263,16 +281,11 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;  // electrode `lane`
     sts_f(a_mir + 128 + lane * 4, ve_mine);
     __syncwarp();
-    float ve_reg[PT > 0 ? PT : 1];
-    if (PT > 0) {
-#pragma unroll
-        for (int e = 0; e < (PT > 0 ? PT : 1); ++e) ve_reg[e] = lds_f(a_mir + 128 + e * 4);
-    }
     if (K > 0) {  // empty caches: a key that hashes to another slot can never hit
-        if (lane < K) sts_u(a_cache + lane * G::ENTRY + 280, lane == 0 ? 1u : 0u);
+        if (lane < K) sts_u(a_cache + lane * ENTB + 260, lane == 0 ? 1u : 0u);
         if (GLOG > 0)
             for (int e = lane; e < (1 << GLOG); e += 32)
-                __stcg(reinterpret_cast<unsigned int *>(gtab + (size_t)e * GENTRY + 280), e == 0 ? 1u : 0u);
+                __stcg(reinterpret_cast<unsigned int *>(gtab + (size_t)e * ENTB + 260), e == 0 ? 1u : 0u);
     }
 
     // ---- initial state
@@ -304,14 +317,15 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     float e_me = 0.0f, top = 0.0f, rest = 0.0f;
     uint32_t ptn = 0;
 
-    uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
     // Loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied:
-    //   pre   exclusive fp64 prefix over the lanes' TOP rates; its 6 mantissa LSBs carry the lane's partner site
-    //   mtop  total mass of the top events; total = mtop + mass of all other events; rtot = 1/total (fp32)
-    //         (+inf for a lane without a positive rate: it can never win the ballot)
-    uint32_t keyv = ~occ;  // first hop: miss
-    double pre = 0.0, mtop = 0.0, total = 0.0;
-    float rtot = 0.0f;
+    //   pre   NORMALISED exclusive fp64 prefix over the lanes' TOP rates (prefix / total rate of the state); its 7
+    //         mantissa LSBs carry the lane's top event: partner acceptor j | 32+e (hole into electrode e) | 64+e
+    //         (hole out of electrode e).  +inf for a lane without a positive rate (it can never win the ballot);
+    //         lane 31 holds the SENTINEL: the normalised mass of all top events -- a uniform above it (0.2 % of the
+    //         hops on C3) falls into the rest of the list.
+    //   rtot  1/total (fp32) for the dwell time
+    uint2 tailv = make_uint2(0u, ~occ);  // {1/total, key}; first hop: miss
+    double pre = 0.0;
     __syncwarp();
 
     int64_t h = 0;
@@ -338,142 +352,158 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
             sts_u4(a_rng + lane * 32 + 16, make_uint4(__float_as_uint(e1), 0u, (uint32_t)__double2loint(u1), (uint32_t)__double2hiint(u1)));
             __syncwarp();
         }
-        for (int q = q0; q < q1; ++q) {
+        uint32_t a_rq = a_rng + (uint32_t)q0 * 16u;
+        const uint32_t a_rq1 = a_rng + (uint32_t)q1 * 16u;
+        for (; a_rq != a_rq1; a_rq += 16u) {
             // ---- event structure of this state: cached, or computed and parked
             bool hit = false;
-            if (K > 0) hit = __all_sync(FULL, keyv == occ);
-            bool swept = false;
+            if (K > 0) hit = __all_sync(FULL, tailv.y == occ);
             if (!hit) {
+                double total;
+                float rtot;
+                // (the fast path moves the mask through a shuffle; REDUX tells the compiler it is warp-uniform again)
+                const uint32_t occu = __reduce_or_sync(FULL, occ);
+                const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
                 bool hit2 = false;
                 unsigned char *gent = nullptr;
                 if (GLOG > 0) {  // second level (global memory, L2): all loads in flight at once, one latency
-                    gent = gtab + (size_t)((occ * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * GENTRY;
+                    gent = gtab + (size_t)((occu * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * ENTB;
                     const double g_pre = __ldcg(reinterpret_cast<const double *>(gent + lane * 8));
-                    const uint4 g0 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // mtop | total
-                    const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 272));  // rtot | pad | key | pad
-                    hit2 = __all_sync(FULL, g1.z == occ);
+                    const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // rtot | key | total
+                    hit2 = __all_sync(FULL, g1.y == occu);
                     if (hit2) {
                         pre = g_pre;
-                        mtop = __hiloint2double((int)g0.y, (int)g0.x);
-                        total = __hiloint2double((int)g0.w, (int)g0.z);
                         rtot = __uint_as_float(g1.x);
+                        total = __hiloint2double((int)g1.w, (int)g1.z);
                     }
                 }
                 if (!hit2) {
                     if (DBG) ++n_miss;
-                    sweep_state<PT>(occ, accm, E64, lane, N, P, nb, ve_reg, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
-                    swept = true;
+                    sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
                     const double incl = scan_d((double)top);
-                    mtop = __shfl_sync(FULL, incl, 31);
+                    const double mtop = __shfl_sync(FULL, incl, 31);
                     double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
                     if (lane == 0) ex = 0.0;
                     double rsum = (double)rest;
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
                     total = mtop + rsum;
-                    rtot = rcp_approx((float)total);
-                    pre = (top > 0.0f) ? __hiloint2double(__double2hiint(ex), (__double2loint(ex) & ~63) | (int)ptn)
-                                       : __longlong_as_double(0x7ff0000000000000LL);
+                    if (__all_sync(FULL, !(total > 0.0))) {  // no transition possible (simulation.go:297 would divide by zero)
+                        dead = true;
+                        break;
+                    }
+                    const double inv = 1.0 / total;
+                    rtot = (float)inv;
+                    const double pn = ex * inv;
+                    const bool occ_me = (occu >> lane) & 1u;
+                    const uint32_t code = (ptn < (uint32_t)N) ? ptn : (ptn - (uint32_t)N + (occ_me ? 32u : 64u));
+                    pre = (top > 0.0f) ? __hiloint2double(__double2hiint(pn), (__double2loint(pn) & ~127) | (int)code) : INF;
+                    if (lane == 31) pre = mtop * inv;
                     if (GLOG > 0) {
                         __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
-                        if (lane == 0) {
+                        if (lane == 0)
                             __stcg(reinterpret_cast<uint4 *>(gent + 256),
-                                   make_uint4((uint32_t)__double2loint(mtop), (uint32_t)__double2hiint(mtop),
-                                              (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
-                            __stcg(reinterpret_cast<uint4 *>(gent + 272), make_uint4(__float_as_uint(rtot), 0u, occ, 0u));
-                        }
+                                   make_uint4(__float_as_uint(rtot), occu, (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
                     }
                 }
-                if (K > 0) {  // install in the first level
-                    sts_d(a_cache + slot * G::ENTRY + lane * 8, pre);
-                    if (lane == 0) {
-                        sts_d(a_cache + slot * G::ENTRY + 256, mtop);
-                        sts_d(a_cache + slot * G::ENTRY + 264, total);
-                        sts_f(a_cache + slot * G::ENTRY + 272, rtot);
-                        sts_u(a_cache + slot * G::ENTRY + 280, occ);
-                    }
+                // install in the first level (without memoisation: a scratch entry that never hits; the slow path and
+                // the replay read the total from it)
+                sts_d(a_ent + lane * 8, pre);
+                tailv = make_uint2(__float_as_uint(rtot), K > 0 ? occu : ~occu);
+                if (lane == 0) {
+                    sts_u2(a_ent + 256, tailv);
+                    sts_d(a_ent + 264, total);
                 }
+                __syncwarp();
             }
 
-            // ---- random variates
-            double r_pick;
+            // ---- random variates: unit exponential for the dwell time (simulation.go:297), uniform for the pick (:164)
+            double u;
             double dtd = 0.0;
             if (!inject) {
-                const uint4 rv = lds_u4(a_rng + q * 16);
-                const float dt = __uint_as_float(rv.x) * rtot;
+                const uint4 rv = lds_u4(a_rq);
+                const float dt = __uint_as_float(rv.x) * __uint_as_float(tailv.x);
                 t_part += dt;
                 if (DBG) dtd = (double)dt;
-                r_pick = __hiloint2double((int)rv.w, (int)rv.z) * total;
+                u = __hiloint2double((int)rv.w, (int)rv.z);
             } else {
-                const int64_t hh = h + (q - q0);
-                dtd = E.stream_e[m * total_hops + hh] / total;          // simulation.go:297
-                r_pick = (double)E.stream_u[m * total_hops + hh] * total;  // simulation.go:164
+                const int64_t hh = h + (int64_t)((a_rq - a_rng) >> 4) - q0;
+                const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
+                dtd = E.stream_e[m * total_hops + hh] / lds_d(a_ent + 264);
+                u = (double)E.stream_u[m * total_hops + hh];
                 t_acc += dtd;
             }
 
             int from = 0, to = 0;
-            uint32_t occ_new = occ;
-            int deo = 0;  // this lane's electrode tally change
-            if (__all_sync(FULL, r_pick < mtop)) {  // (a vote, so that the compiler sees a warp-uniform branch)
-                // ---- the common case (C3: 99.8 % of the hops): one of the 32 cached top events.
-                //      lane = the highest positive one whose interval starts below the threshold.
-                const uint32_t bal = __ballot_sync(FULL, pre < r_pick);
-                // (every loop exit is decided by a vote: the compiler must be able to see that the warp stays converged)
-                if (!bal) {  // no transition possible (simulation.go:297 would divide by zero), or NaN
-                    dead = true;
-                    break;
-                }
-                const int istar = 31 - __clz(bal);
-                const int partner = (int)bcast_u((uint32_t)__double2loint(pre) & 63u, istar, lane);
-                // apply the hop (simulation.go:107-130): lane istar's site flips; the partner is an acceptor or an electrode
-                if ((occ >> istar) & 1u) {  // istar -> partner
-                    occ_new = occ & ~(1u << istar);
-                    if (partner < N) occ_new |= 1u << partner;
-                    else deo = (int)(lane == partner - N);
-                    if (DBG) { from = istar; to = partner; }
-                } else {                    // electrode partner -> istar
-                    occ_new = occ | (1u << istar);
-                    deo = -(int)(lane == partner - N);
-                    if (DBG) { from = partner; to = istar; }
+            uint32_t occ_new;
+            const uint32_t bal = __ballot_sync(FULL, pre < u);
+            if (__builtin_expect((int)bal > 0, 1)) {
+                // ---- the common case (C3: 99.8 % of the hops): one of the cached top events, the sentinel did not fire.
+                //      lane = the highest positive one whose interval starts below the uniform.  Branch-free update
+                //      (simulation.go:107-130): lane istar's site flips; an acceptor partner flips too; an electrode
+                //      partner (code >= 32: the clamped bit mask is 0) gains or loses one hole.
+                const int istar = bfind_u(bal);
+                const uint32_t code = (uint32_t)__shfl_sync(FULL, __double2loint(pre), istar) & 127u;
+                occ_new = occ ^ (bit_clamp((uint32_t)istar) | bit_clamp(code));
+                asm("{ .reg .pred p, q; .reg .u32 t;\n"
+                    "  sub.u32 t, %1, %2;\n"
+                    "  setp.eq.u32 p, t, 32;\n"
+                    "  setp.eq.u32 q, t, 64;\n"
+                    "  @p add.s32 %0, %0, 1;\n"
+                    "  @q add.s32 %0, %0, -1; }"
+                    : "+r"(eoc)
+                    : "r"(code), "r"(lane));
+                if (DBG) {
+                    if (code < 32u) { from = istar; to = (int)code; }
+                    else if (code < 64u) { from = istar; to = N + (int)code - 32; }
+                    else { from = N + (int)code - 64; to = istar; }
                 }
             } else {
                 // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
-                if (!swept) {
-                    if (DBG) ++n_miss;
-                    sweep_state<PT>(occ, accm, E64, lane, N, P, nb, ve_reg, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                const uint32_t occu = __reduce_or_sync(FULL, occ);
+                occ_new = occu;
+                int deo = 0;
+                // (rare enough that the sweep is simply repeated, even when this very hop already missed)
+                if (DBG && hit) ++n_miss;
+                sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
+                const double total = lds_d(a_ent + 264);
+                int istar = -1;
+                float rf = BIGE;
+                int skip = -1;
+                if (bal >> 31) {
+                    const double mtopn = __shfl_sync(FULL, pre, 31);
+                    const double rres = (u - mtopn) * total;
+                    const double incl = scan_d((double)rest);
+                    double ex = __shfl_up_sync(FULL, incl, 1);
+                    if (lane == 0) ex = 0.0;
+                    const uint32_t rpos = __ballot_sync(FULL, rest > 0.0f);
+                    uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
+                    if (!b2) b2 = rpos & (0u - rpos);
+                    if (b2) {
+                        istar = 31 - __clz(b2);
+                        rf = __shfl_sync(FULL, (float)(rres - ex), istar);
+                        skip = (int)bcast_u(ptn, istar, lane);
+                    }
                 }
-                const double rres = r_pick - mtop;
-                const double incl = scan_d((double)rest);
-                double ex = __shfl_up_sync(FULL, incl, 1);
-                if (lane == 0) ex = 0.0;
-                const uint32_t rpos = __ballot_sync(FULL, rest > 0.0f);
-                uint32_t bal = __ballot_sync(FULL, ex < rres) & rpos;
-                if (!bal) bal = rpos & (0u - rpos);
-                int istar;
-                float rf;
-                int skip;
-                if (__any_sync(FULL, bal != 0u)) {
-                    istar = 31 - __clz(bal);
-                    rf = __shfl_sync(FULL, (float)(rres - ex), istar);
-                    skip = (int)bcast_u(ptn, istar, lane);
-                } else {  // no mass outside the top events (rounding): take the last top event instead
-                    const uint32_t posu = __ballot_sync(FULL, pre < __longlong_as_double(0x7ff0000000000000LL));
+                if (istar < 0) {
+                    // no mass outside the top events (rounding), or a uniform of exactly 0 (injected stream): take the
+                    // last (first) top event instead
+                    const uint32_t posu = __ballot_sync(FULL, pre < INF) & 0x7fffffffu;
                     if (!posu) {
                         dead = true;
                         break;
                     }
-                    istar = 31 - __clz(posu);
-                    rf = BIGE;
-                    skip = -1;
+                    istar = (bal >> 31) ? 31 - __clz(posu) : __ffs(posu) - 1;
                 }
-                const bool rowocc = __any_sync(FULL, (occ >> istar) & 1u);
+                const bool rowocc = (occu >> istar) & 1u;
                 const float e_star = lds_f(a_mir + istar * 4);
                 if (rowocc) {
                     from = istar;
                     to = -1;
                     int lastA = -1;
                     float sA = 0.0f;
-                    const uint32_t emp = ~occ & accm;
+                    const uint32_t emp = ~occu & accm;
                     if (emp) {  // acceptor targets: istar -> empty `lane`
                         float rr = 0.0f;
                         if (((emp >> lane) & 1u) && lane != skip) {
@@ -516,19 +546,21 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                 else deo -= (int)(lane == from - N);
                 if (to < N) occ_new |= (1u << to);
                 else deo += (int)(lane == to - N);
+                eoc += deo;
             }
 
             // ---- tallies (simulation.go:309-317: pre-hop occupation, antisymmetric traffic)
             if (DBG && h >= prehops) {
                 if ((occ >> lane) & 1u) occtime += dtd;
                 if (lane == 0) {
+                    const int64_t hh = h + (int64_t)((a_rq - a_rng) >> 4) - q0;
                     if (E.traffic) {
                         double *tr = E.traffic + m * (int64_t)S * S;
                         tr[from * S + to] += 1.0;
                         tr[to * S + from] -= 1.0;
                     }
                     if (E.trace) {
-                        int32_t *tp = E.trace + (m * E.hops + (h + (q - q0) - prehops)) * 2;
+                        int32_t *tp = E.trace + (m * E.hops + (hh - prehops)) * 2;
                         tp[0] = from;
                         tp[1] = to;
                     }
@@ -537,17 +569,10 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
 
             // ---- the new state; the energies follow from the new mask when next needed
             occ = occ_new;
-            eoc += deo;
-            if (K > 0) {  // prefetch the next state's cache line (lane 0 may have written it in this very hop)
-                __syncwarp();
-                slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-                pre = lds_d(a_cache + slot * G::ENTRY + lane * 8);
-                const uint4 t0 = lds_u4(a_cache + slot * G::ENTRY + 256);  // mtop | total
-                const uint4 t1 = lds_u4(a_cache + slot * G::ENTRY + 272);  // rtot | pad | key | pad
-                mtop = __hiloint2double((int)t0.y, (int)t0.x);
-                total = __hiloint2double((int)t0.w, (int)t0.z);
-                rtot = __uint_as_float(t1.x);
-                keyv = t1.z;
+            if (K > 0) {  // prefetch the next state's cache line
+                const uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
+                pre = lds_d(slot * ENTB + a_cache_lane);
+                tailv = lds_u2(slot * ENTB + a_cache_tail);  // rtot | key
             }
         }
         h = hend;
@@ -560,8 +585,9 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     }
 
     // ---- results
+    occ = __reduce_or_sync(FULL, occ);
     t_acc += (double)t_part;
-    if (dead) t_acc = __longlong_as_double(0x7ff0000000000000LL);  // +inf, as time_step = e/0 would give
+    if (dead) t_acc = INF;  // +inf, as time_step = e/0 would give
     if (lane == 0) E.time[m] = t_acc;
     if (lane < P) E.electrode_occ[m * P + lane] = (int64_t)eoc;
     if (lane < N) {
@@ -651,13 +677,13 @@ static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int l
 
 // logk: log2(first-level cache slots per warp); -1 disables the memoisation (same code path, every hop a miss).
 // plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the
-// second-level table E.gtab = warp_slots * 2^E.gtab_log * 288 bytes from it.
+// second-level table E.gtab = warp_slots * 2^E.gtab_log * 272 bytes from it.
 cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
     if (E.B <= 0) {
         if (plan) plan->warp_slots = 0;
         return cudaSuccess;
     }
-    if (L.N > 32 || L.P > 32 || L.pitchf != 33) return cudaErrorInvalidValue;
+    if (L.N > 31 || L.P > 32 || L.pitchf != 33) return cudaErrorInvalidValue;
     if (L.P == 8) return launch_memo_p<8>(L, E, logk, st, launches, plan);
     if (L.P == 2) return launch_memo_p<2>(L, E, logk, st, launches, plan);
     return launch_memo_p<0>(L, E, logk, st, launches, plan);

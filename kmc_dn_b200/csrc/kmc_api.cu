@@ -44,7 +44,7 @@ struct kmcb200_layout {
     // grow-only device workspace for host-pointer calls
     void *ws = nullptr;
     size_t ws_bytes = 0;
-    // second-level state cache of the memoised kernel (warp_slots x 2^glog x 288 B), grow-only
+    // second-level state cache of the memoised kernel (warp_slots x 2^glog x 272 B), grow-only
     void *gtab = nullptr;
     size_t gtab_bytes = 0;
     unsigned long long *queue = nullptr;  // member work queue of the persistent kernel
@@ -300,7 +300,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     if (prob) le = launch_prob(D, E, st, &launches);
     else if (exact) le = launch_exact(D, E, st, &launches);
     else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
-    else if (D.N <= 32 && !getenv("KMCB200_NO_MEMO_KERNEL")) {
+    else if (D.N <= 31 && !getenv("KMCB200_NO_MEMO_KERNEL")) {
         int logk = 4, glog = 8;
         if (const char *ev = getenv("KMCB200_MEMO_LOGK")) logk = atoi(ev);
         if (const char *ev = getenv("KMCB200_GTAB_LOG")) glog = atoi(ev);
@@ -311,7 +311,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             MemoPlan plan{0};
             le = launch_memo(D, E, logk, st, nullptr, &plan);
             if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-            const size_t bytes = ((size_t)plan.warp_slots << glog) * 288;
+            const size_t bytes = ((size_t)plan.warp_slots << glog) * 272;
             if (bytes > lay->gtab_bytes) {
                 if (lay->gtab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->gtab)); lay->gtab = nullptr; lay->gtab_bytes = 0; }
                 CU(cudaMalloc(&lay->gtab, bytes));

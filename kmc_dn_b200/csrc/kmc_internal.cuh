@@ -41,7 +41,7 @@ struct EnsembleDev {
     double *prob_occupation, *prob_electrode_occ;  // MODE_PROB: fractional occupations [B,N], electrode tallies [B,P]
     double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
     unsigned long long *queue;  // memoised kernel: member work queue (zeroed before the launch)
-    unsigned char *gtab;  // memoised kernel: second-level cache, warp_slots * 2^gtab_log entries of 288 B (or null)
+    unsigned char *gtab;  // memoised kernel: second-level cache, warp_slots * 2^gtab_log entries of 272 B (or null)
     int gtab_log;         // log2(entries per warp slot); 0 = no second level
 };
 
