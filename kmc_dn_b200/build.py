@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 UNITS = {
     "hop_fast.cu": [],
     "hop_memo.cu": [],
+    "hop_wide.cu": [],
     "hop_reforder.cu": [],
     "hop_exact.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "hop_prob.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],

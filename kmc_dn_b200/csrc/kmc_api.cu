@@ -300,8 +300,10 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     if (prob) le = launch_prob(D, E, st, &launches);
     else if (exact) le = launch_exact(D, E, st, &launches);
     else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
-    else if (D.N <= 31 && !getenv("KMCB200_NO_MEMO_KERNEL")) {
-        int logk = 4, glog = 8;
+    else if (!getenv("KMCB200_NO_MEMO_KERNEL")) {
+        // memoised production kernels: hop_memo.cu (N <= 31: one mask word, sentinel lane) / hop_wide.cu (N <= 256)
+        const bool narrow = D.N <= 31;
+        int logk = 4, glog = narrow ? 8 : 9;
         if (const char *ev = getenv("KMCB200_MEMO_LOGK")) logk = atoi(ev);
         if (const char *ev = getenv("KMCB200_GTAB_LOG")) glog = atoi(ev);
         if (a->flags & KMCB200_FLAG_NO_MEMO) logk = -1;
@@ -309,20 +311,22 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         E.gtab = nullptr; E.gtab_log = 0;
         if (glog > 0) {  // second-level cache table: one region per persistent warp slot, kept with the layout
             MemoPlan plan{0};
-            le = launch_memo(D, E, logk, st, nullptr, &plan);
+            le = narrow ? launch_memo(D, E, logk, st, nullptr, &plan) : launch_wide(D, E, logk, st, nullptr, &plan);
             if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-            const size_t bytes = ((size_t)plan.warp_slots << glog) * 272;
+            const size_t bytes = ((size_t)plan.warp_slots << glog) * (narrow ? 272 : 448);
             if (bytes > lay->gtab_bytes) {
                 if (lay->gtab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->gtab)); lay->gtab = nullptr; lay->gtab_bytes = 0; }
                 CU(cudaMalloc(&lay->gtab, bytes));
                 lay->gtab_bytes = bytes;
             }
+            // hop_wide.cu validates entries by a per-member generation tag: the table must start out zeroed
+            if (!narrow) CU(cudaMemsetAsync(lay->gtab, 0, bytes, st));
             E.gtab = (unsigned char *)lay->gtab; E.gtab_log = glog;
         }
         if (!lay->queue) CU(cudaMalloc((void **)&lay->queue, 256));
         CU(cudaMemsetAsync(lay->queue, 0, 256, st));
         E.queue = lay->queue;
-        le = launch_memo(D, E, logk, st, &launches);
+        le = narrow ? launch_memo(D, E, logk, st, &launches) : launch_wide(D, E, logk, st, &launches);
     } else le = launch_fast(D, E, st, &launches);
     g_launches += launches;
     if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));

@@ -50,6 +50,8 @@ cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t s
 struct MemoPlan { int64_t warp_slots; };
 cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
                         MemoPlan *plan_only = nullptr);
+cudaError_t launch_wide(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
+                        MemoPlan *plan_only = nullptr);
 cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_prob(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);

@@ -32,10 +32,8 @@ def gpu_rate(w, scale=1.0, reps=2):
         dt = time.perf_counter() - t0
         best = max(best, len(w["V"]) * (hops + pre) / dt)
     idx = np.linspace(0, len(w["V"]) - 1, min(2048, len(w["V"]))).astype(np.int64)
-    miss = None
-    if lt.N <= 32:
-        s = lay.run(hops, w["kT"][idx], w["V"][idx], want_misses=True, **kw)
-        miss = float(s["misses"].mean() / (hops + pre))
+    s = lay.run(hops, w["kT"][idx], w["V"][idx], want_misses=True, **kw)
+    miss = float(s["misses"].mean() / (hops + pre))
     lay.close()
     finite = float(np.isfinite(r["time"]).mean())
     return best, miss, finite, hops, pre
@@ -71,6 +69,9 @@ def main():
     ap.add_argument("--tag", default="r01")
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=6.0)
+    ap.add_argument("--only", default="", help="comma-separated config names (default: all)")
+    ap.add_argument("--no-cpu", action="store_true", help="GPU numbers only")
+    ap.add_argument("--out-dir", default=os.path.join(ROOT, "profiles"))
     args = ap.parse_args()
     from kmc_dn_b200 import workloads
     q = args.quick
@@ -83,8 +84,15 @@ def main():
         ("C5", workloads.c5_scaling(N=256, M=25, B=1024 if q else 8192), 1.0),
     ]
     rows = []
+    only = [x for x in args.only.split(",") if x]
     for name, w, scale in configs:
+        if only and name not in only:
+            continue
         g, miss, finite, hops, pre = gpu_rate(w, scale)
+        if args.no_cpu:
+            print(json.dumps(dict(config=name, workload=w["name"], members=int(len(w["V"])), hops=hops, prehops=pre,
+                                  gpu_hops_per_s=g, state_cache_miss_rate=miss, finite_fraction=finite)), flush=True)
+            continue
         c_cache, Bc, hc = cpu_rate(w, args.cpu_seconds, "go", True, scale)
         c_nocache, _, _ = cpu_rate(w, args.cpu_seconds / 2, "go", False, scale)
         c_py, _, _ = cpu_rate(w, args.cpu_seconds / 2, "py", True, scale)
@@ -95,7 +103,9 @@ def main():
                    speedup_vs_cached=g / c_cache, speedup_vs_uncached=g / c_nocache, speedup_vs_numba_port=g / c_py)
         rows.append(row)
         print(json.dumps(row), flush=True)
-    out = os.path.join(ROOT, "profiles", f"configs_{args.tag}")
+    if args.no_cpu:
+        return
+    out = os.path.join(args.out_dir, f"configs_{args.tag}")
     json.dump(rows, open(out + ".json", "w"), indent=1)
     with open(out + ".md", "w") as f:
         f.write("| config | members x hops | B200 x1 hops/s (e2e) | miss rate | CPU Go-port +cache | Go-port no cache | numba-port | "

@@ -263,15 +263,16 @@ def test_fast_kernel_ensemble_mean_within_confidence_interval_of_oracle(golden_p
     RNG).  |mean_gpu - mean_cpu| <= 4.5 * sqrt(se_gpu^2 + se_cpu^2) per electrode (two-sample z, ~1e-5 false
     alarm per electrode)."""
     from oracle import oracle
-    for name in ("fx_rnd_min_max_0", "c2_grid_N16_P8", "n5_p3_hot"):
-        c = golden_py[name]
-        B, hops = 256, 20000
+    for name in ("fx_rnd_min_max_0", "c2_grid_N16_P8", "n5_p3_hot", "N48_P8", "N100_P5"):
+        c = golden_py[name] if name in golden_py else \
+            {"N48_P8": synthetic_layout(48, 8, 1), "N100_P5": synthetic_layout(100, 5, 2, kT=3.0, I_0=30.0)}[name]
+        B, hops = (256, 20000) if c["N"] <= 32 else (192, 6000)
         E = np.tile(c["E_constant"], (B, 1)); V = np.tile(c["electrode_v"], (B, 1))
         lay = _layout(c)
         g = lay.run(hops, c["kT"], V, E_constant=E, occupation0=c["occupation"], prehops=2000, seed=5)
         o = oracle.go_ensemble(c["N"], c["P"], c["nu"], c["kT"], c["I_0"], c["R"], c["distances"], E,
-                               c["transitions_constant"], V, hops + 2000, variant=1, use_cache=True,
-                               occupation0=c["occupation"], seed0=99)
+                               c["transitions_constant"], V, hops + 2000, variant=1, use_cache=c["N"] <= 64,
+                               occupation0=c["occupation"], seed0=99)  # (getKey drops acceptors beyond 64: no cache there)
         # compare net carrier counts per unit time; the oracle has no prehops, so use equal total lengths
         g2 = lay.run(hops + 2000, c["kT"], V, E_constant=E, occupation0=c["occupation"], seed=6)
         cg = g2["electrode_occupation"] / g2["time"][:, None]
@@ -303,7 +304,10 @@ def test_state_memoisation_is_transparent(golden_py, fixtures_subset):
     (KMCB200_FLAG_NO_MEMO) every trajectory is bit-identical -- hop sequence, time, tallies, occupation --
     and the cache really is used (rate structures evaluated on a small fraction of the hops)."""
     cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
-             "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"], "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"])}
+             "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"], "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"]),
+             # hop_wide.cu: multi-word masks, 1 / 2 / 4 / 8 acceptors per lane
+             "N32_P8": synthetic_layout(32, 8, 4), "N48_P8": synthetic_layout(48, 8, 1),
+             "N100_P5": synthetic_layout(100, 5, 2, kT=3.0, I_0=30.0), "N256_P8": synthetic_layout(256, 8, 3, fill=0.9)}
     for name, c in cases.items():
         B, hops = 24, 6000
         V = np.tile(c["electrode_v"], (B, 1)) + np.linspace(0, 5, B)[:, None]
@@ -322,6 +326,25 @@ def test_state_memoisation_is_transparent(golden_py, fixtures_subset):
         np.testing.assert_array_equal(a["avg_occupation"], b["avg_occupation"])
         assert (b["misses"] == hops + 500).all(), name
         assert (a["misses"] < b["misses"]).all() and a["misses"].mean() < 0.9 * (hops + 500), (name, a["misses"].mean())
+
+
+def test_wide_memo_kernel_agrees_with_general_kernel(monkeypatch):
+    """hop_wide.cu (memoised, top events first) and hop_fast.cu (every hop a full sweep, lane-major list) sample the
+    same Markov chain: ensemble means of time and electrode currents agree (two-sample z) on the scaling layout."""
+    c = synthetic_layout(256, 8, 3, fill=0.9)
+    B, hops = 512, 4000
+    V = np.tile(c["electrode_v"], (B, 1)); E = np.tile(c["E_constant"], (B, 1))
+    lay = _layout(c)
+    a = lay.run(hops, c["kT"], V, E_constant=E, occupation0=c["occupation"], seed=31, want_misses=True)
+    monkeypatch.setenv("KMCB200_NO_MEMO_KERNEL", "1")
+    b = lay.run(hops, c["kT"], V, E_constant=E, occupation0=c["occupation"], seed=32)
+    monkeypatch.delenv("KMCB200_NO_MEMO_KERNEL")
+    lay.close()
+    assert a["misses"].mean() < 0.5 * hops, a["misses"].mean()  # the cache is used
+    za = np.abs(a["time"].mean() - b["time"].mean()) / np.sqrt(a["time"].var() / B + b["time"].var() / B)
+    ca = a["electrode_occupation"] / a["time"][:, None]; cb = b["electrode_occupation"] / b["time"][:, None]
+    z = np.abs(ca.mean(0) - cb.mean(0)) / np.sqrt(ca.var(0) / B + cb.var(0) / B + 1e-300)
+    assert za < 4.5 and (z < 4.5).all(), (za, z)
 
 
 def test_superposition_matvec_equals_explicit_E_constant(fixtures_subset):
@@ -381,19 +404,30 @@ def test_edge_cases(golden_py):
 
 def test_record_tallies_of_fast_kernel(golden_py):
     """traffic is the antisymmetric net count and average_occupation the pre-hop occupied time (simulation.go:309-317)."""
-    c = golden_py["n5_p3_hot"]
-    lay = _layout(c)
-    hops = 20000
-    r = lay.run(hops, c["kT"], c["electrode_v"][None], E_constant=c["E_constant"][None], record=True, trace=True,
-                want_occupation=True, seed=12)
-    S = c["N"] + c["P"]
-    tr = np.zeros((S, S))
-    np.add.at(tr, (r["trace"][0][:, 0], r["trace"][0][:, 1]), 1.0)
-    np.testing.assert_array_equal(r["traffic"][0], tr - tr.T)
-    net_in = -(tr - tr.T).sum(1)[c["N"]:]  # holes arriving at each electrode
-    np.testing.assert_array_equal(r["electrode_occupation"][0], net_in.astype(np.int64))
-    assert (r["avg_occupation"][0] <= r["time"][0] * (1 + 1e-6)).all() and (r["avg_occupation"][0] >= 0).all()
-    lay.close()
+    for c in (golden_py["n5_p3_hot"], synthetic_layout(48, 8, 1), synthetic_layout(200, 8, 6, fill=0.9)):
+        lay = _layout(c)
+        hops = 20000
+        r = lay.run(hops, c["kT"], c["electrode_v"][None], E_constant=c["E_constant"][None], record=True, trace=True,
+                    occupation0=c["occupation"], want_occupation=True, want_site_energies=True, seed=12)
+        N, S = c["N"], c["N"] + c["P"]
+        tr = np.zeros((S, S))
+        np.add.at(tr, (r["trace"][0][:, 0], r["trace"][0][:, 1]), 1.0)
+        np.testing.assert_array_equal(r["traffic"][0], tr - tr.T)
+        net_in = -(tr - tr.T).sum(1)[N:]  # holes arriving at each electrode
+        np.testing.assert_array_equal(r["electrode_occupation"][0], net_in.astype(np.int64))
+        assert (r["avg_occupation"][0] <= r["time"][0] * (1 + 1e-6)).all() and (r["avg_occupation"][0] >= 0).all()
+        # replaying the trace on the host: every hop allowed (source occupied / target empty), final mask as reported,
+        # final energies = from-scratch energies of that mask
+        occ = c["occupation"].copy()
+        for f, t in r["trace"][0]:
+            if f < N:
+                assert occ[f]; occ[f] = False
+            if t < N:
+                assert not occ[t]; occ[t] = True
+        np.testing.assert_array_equal(r["occupation"][0].astype(bool), occ)
+        se, _ = lay.probe_rates(c["E_constant"], c["electrode_v"], c["kT"], occ)
+        np.testing.assert_array_equal(r["site_energies"][0].astype(np.float32), se)
+        lay.close()
 
 
 # ------------------------------------------------------------------ the drop-in exports
