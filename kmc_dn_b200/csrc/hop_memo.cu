@@ -27,9 +27,11 @@
 //             partner site and the direction -- in the 7 mantissa LSBs), lane 31 = the normalised mass of these top
 //             events (sentinel), the fp32 reciprocal of the total rate and the fp64 total (272 B)
 //
-// Hit:  the sweep and the fp64 scan are skipped; the hop costs the lookup, ONE ballot of prefix < uniform (the
-//       sentinel lane routes the 0.2 % of the hops that fall outside the top events to the exact slow path), one
-//       shuffle for the winning lane's event code and a branch-free update of the mask and the electrode tallies.
+// Hit:  the sweep and the fp64 scan are skipped; the hop costs ONE ballot of (key matches && prefix < uniform) on the
+//       speculatively prefetched line -- an empty ballot means another state's line, the sentinel lane (the 0.2 % of
+//       the hops that fall outside the top events take the exact slow path) or a dead state --, one shuffle for the
+//       winning lane's event code and a branch-free update of the mask and the electrode tallies: 29 SASS
+//       instructions per hop.
 // Miss: sweep + scan, then the prefix is parked in the slot.
 // Memoising a pure function cannot change a result: with the cache disabled (LOGK = -1 instantiation,
 // KMCB200_FLAG_NO_MEMO) the kernel produces bit-identical trajectories (tests/test_gpu_parity.py).
@@ -225,6 +227,29 @@ __device__ __forceinline__ uint32_t bit_clamp(uint32_t n) {
 }
 __device__ __forceinline__ void sts_u2(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y)); }
 
+// The common case of a hop: one of the cached top events.  lane istar = the highest one whose interval starts below
+// the uniform; branch-free update (simulation.go:107-130): istar's site flips; an acceptor partner flips too; an
+// electrode partner (code >= 32: the clamped bit mask is 0) gains (32+e) or loses (64+e) one hole.
+template <bool DBG>
+__device__ __forceinline__ void apply_top(uint32_t bal, double pre, int lane, int N, uint32_t &occ, int &eoc, int &from, int &to) {
+    const int istar = bfind_u(bal);
+    const uint32_t code = (uint32_t)__shfl_sync(FULL, __double2loint(pre), istar) & 127u;
+    occ ^= bit_clamp((uint32_t)istar) | bit_clamp(code);
+    asm("{ .reg .pred p, q; .reg .u32 t;\n"
+        "  sub.u32 t, %1, %2;\n"
+        "  setp.eq.u32 p, t, 32;\n"
+        "  setp.eq.u32 q, t, 64;\n"
+        "  @p add.s32 %0, %0, 1;\n"
+        "  @q add.s32 %0, %0, -1; }"
+        : "+r"(eoc)
+        : "r"(code), "r"(lane));
+    if (DBG) {
+        if (code < 32u) { from = istar; to = (int)code; }
+        else if (code < 64u) { from = istar; to = N + (int)code - 32; }
+        else { from = N + (int)code - 64; to = istar; }
+    }
+}
+
 template <int PT, int LOGK, bool DBG>
 __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = MemoGeom<LOGK, PT>;
@@ -254,7 +279,6 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
     const uint32_t a_mir = wb, a_rng = wb + G::MIRB, a_cache = wb + G::MIRB + 1024;
-    const uint32_t a_cache_lane = a_cache + lane * 8u, a_cache_tail = a_cache + 256u;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
@@ -348,210 +372,214 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
             const double u0 = ((double)r.y + 0.5) * 2.3283064365386963e-10;
             const double u1 = ((double)r.w + 0.5) * 2.3283064365386963e-10;
             __syncwarp();
-            sts_u4(a_rng + lane * 32, make_uint4(__float_as_uint(e0), 0u, (uint32_t)__double2loint(u0), (uint32_t)__double2hiint(u0)));
-            sts_u4(a_rng + lane * 32 + 16, make_uint4(__float_as_uint(e1), 0u, (uint32_t)__double2loint(u1), (uint32_t)__double2hiint(u1)));
+            sts_u4(a_rng + lane * 32, make_uint4((uint32_t)__double2loint(u0), (uint32_t)__double2hiint(u0), __float_as_uint(e0), 0u));
+            sts_u4(a_rng + lane * 32 + 16, make_uint4((uint32_t)__double2loint(u1), (uint32_t)__double2hiint(u1), __float_as_uint(e1), 0u));
             __syncwarp();
         }
         uint32_t a_rq = a_rng + (uint32_t)q0 * 16u;
         const uint32_t a_rq1 = a_rng + (uint32_t)q1 * 16u;
         for (; a_rq != a_rq1; a_rq += 16u) {
-            // ---- event structure of this state: cached, or computed and parked
-            bool hit = false;
-            if (K > 0) hit = __all_sync(FULL, tailv.y == occ);
-            if (!hit) {
-                double total;
-                float rtot;
-                // (the fast path moves the mask through a shuffle; REDUX tells the compiler it is warp-uniform again)
-                const uint32_t occu = __reduce_or_sync(FULL, occ);
-                const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
-                bool hit2 = false;
-                unsigned char *gent = nullptr;
-                if (GLOG > 0) {  // second level (global memory, L2): all loads in flight at once, one latency
-                    gent = gtab + (size_t)((occu * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * ENTB;
-                    const double g_pre = __ldcg(reinterpret_cast<const double *>(gent + lane * 8));
-                    const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // rtot | key | total
-                    hit2 = __all_sync(FULL, g1.y == occu);
-                    if (hit2) {
-                        pre = g_pre;
-                        rtot = __uint_as_float(g1.x);
-                        total = __hiloint2double((int)g1.w, (int)g1.z);
-                    }
-                }
-                if (!hit2) {
-                    if (DBG) ++n_miss;
-                    sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
-                    const double incl = scan_d((double)top);
-                    const double mtop = __shfl_sync(FULL, incl, 31);
-                    double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
-                    if (lane == 0) ex = 0.0;
-                    double rsum = (double)rest;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
-                    total = mtop + rsum;
-                    if (__all_sync(FULL, !(total > 0.0))) {  // no transition possible (simulation.go:297 would divide by zero)
-                        dead = true;
-                        break;
-                    }
-                    const double inv = 1.0 / total;
-                    rtot = (float)inv;
-                    const double pn = ex * inv;
-                    const bool occ_me = (occu >> lane) & 1u;
-                    const uint32_t code = (ptn < (uint32_t)N) ? ptn : (ptn - (uint32_t)N + (occ_me ? 32u : 64u));
-                    pre = (top > 0.0f) ? __hiloint2double(__double2hiint(pn), (__double2loint(pn) & ~127) | (int)code) : INF;
-                    if (lane == 31) pre = mtop * inv;
-                    if (GLOG > 0) {
-                        __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
-                        if (lane == 0)
-                            __stcg(reinterpret_cast<uint4 *>(gent + 256),
-                                   make_uint4(__float_as_uint(rtot), occu, (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
-                    }
-                }
-                // install in the first level (without memoisation: a scratch entry that never hits; the slow path and
-                // the replay read the total from it)
-                sts_d(a_ent + lane * 8, pre);
-                tailv = make_uint2(__float_as_uint(rtot), K > 0 ? occu : ~occu);
-                if (lane == 0) {
-                    sts_u2(a_ent + 256, tailv);
-                    sts_d(a_ent + 264, total);
-                }
-                __syncwarp();
-            }
-
             // ---- random variates: unit exponential for the dwell time (simulation.go:297), uniform for the pick (:164)
-            double u;
-            double dtd = 0.0;
+            double u, dtd = 0.0;
+            float ek = 0.0f;
             if (!inject) {
                 const uint4 rv = lds_u4(a_rq);
-                const float dt = __uint_as_float(rv.x) * __uint_as_float(tailv.x);
-                t_part += dt;
-                if (DBG) dtd = (double)dt;
-                u = __hiloint2double((int)rv.w, (int)rv.z);
+                ek = __uint_as_float(rv.z);
+                u = __hiloint2double((int)rv.y, (int)rv.x);
             } else {
                 const int64_t hh = h + (int64_t)((a_rq - a_rng) >> 4) - q0;
-                const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
-                dtd = E.stream_e[m * total_hops + hh] / lds_d(a_ent + 264);
                 u = (double)E.stream_u[m * total_hops + hh];
-                t_acc += dtd;
             }
 
+            // ---- speculative pick on the prefetched line: the ballot is empty if the line belongs to another state
+            //      (all lanes see the same key), if the sentinel fired, or if nothing can happen
             int from = 0, to = 0;
-            uint32_t occ_new;
-            const uint32_t bal = __ballot_sync(FULL, pre < u);
+            const uint32_t occ_old = occ;
+            uint32_t bal = __ballot_sync(FULL, (K > 0 && !inject && tailv.y == occ) && pre < u);
             if (__builtin_expect((int)bal > 0, 1)) {
-                // ---- the common case (C3: 99.8 % of the hops): one of the cached top events, the sentinel did not fire.
-                //      lane = the highest positive one whose interval starts below the uniform.  Branch-free update
-                //      (simulation.go:107-130): lane istar's site flips; an acceptor partner flips too; an electrode
-                //      partner (code >= 32: the clamped bit mask is 0) gains or loses one hole.
-                const int istar = bfind_u(bal);
-                const uint32_t code = (uint32_t)__shfl_sync(FULL, __double2loint(pre), istar) & 127u;
-                occ_new = occ ^ (bit_clamp((uint32_t)istar) | bit_clamp(code));
-                asm("{ .reg .pred p, q; .reg .u32 t;\n"
-                    "  sub.u32 t, %1, %2;\n"
-                    "  setp.eq.u32 p, t, 32;\n"
-                    "  setp.eq.u32 q, t, 64;\n"
-                    "  @p add.s32 %0, %0, 1;\n"
-                    "  @q add.s32 %0, %0, -1; }"
-                    : "+r"(eoc)
-                    : "r"(code), "r"(lane));
-                if (DBG) {
-                    if (code < 32u) { from = istar; to = (int)code; }
-                    else if (code < 64u) { from = istar; to = N + (int)code - 32; }
-                    else { from = N + (int)code - 64; to = istar; }
-                }
+                t_part = fmaf(ek, __uint_as_float(tailv.x), t_part);
+                if (DBG) dtd = (double)(ek * __uint_as_float(tailv.x));
+                apply_top<DBG>(bal, pre, lane, N, occ, eoc, from, to);
             } else {
-                // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
-                const uint32_t occu = __reduce_or_sync(FULL, occ);
-                occ_new = occu;
-                int deo = 0;
-                // (rare enough that the sweep is simply repeated, even when this very hop already missed)
-                if (DBG && hit) ++n_miss;
-                sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
-                const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
-                const double total = lds_d(a_ent + 264);
-                int istar = -1;
-                float rf = BIGE;
-                int skip = -1;
-                if (bal >> 31) {
-                    const double mtopn = __shfl_sync(FULL, pre, 31);
-                    const double rres = (u - mtopn) * total;
-                    const double incl = scan_d((double)rest);
-                    double ex = __shfl_up_sync(FULL, incl, 1);
-                    if (lane == 0) ex = 0.0;
-                    const uint32_t rpos = __ballot_sync(FULL, rest > 0.0f);
-                    uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
-                    if (!b2) b2 = rpos & (0u - rpos);
-                    if (b2) {
-                        istar = 31 - __clz(b2);
-                        rf = __shfl_sync(FULL, (float)(rres - ex), istar);
-                        skip = (int)bcast_u(ptn, istar, lane);
+                // ---- event structure of this state: cached after all, or computed and parked
+                bool hit = false;
+                if (K > 0) hit = __all_sync(FULL, tailv.y == occ);
+                if (!hit) {
+                    double total;
+                    float rtot;
+                    // (the fast path moves the mask through a shuffle; REDUX tells the compiler it is warp-uniform again)
+                    const uint32_t occu = __reduce_or_sync(FULL, occ);
+                    const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
+                    bool hit2 = false;
+                    unsigned char *gent = nullptr;
+                    if (GLOG > 0) {  // second level (global memory, L2): all loads in flight at once, one latency
+                        gent = gtab + (size_t)((occu * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * ENTB;
+                        const double g_pre = __ldcg(reinterpret_cast<const double *>(gent + lane * 8));
+                        const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // rtot | key | total
+                        hit2 = __all_sync(FULL, g1.y == occu);
+                        if (hit2) {
+                            pre = g_pre;
+                            rtot = __uint_as_float(g1.x);
+                            total = __hiloint2double((int)g1.w, (int)g1.z);
+                        }
                     }
+                    if (!hit2) {
+                        if (DBG) ++n_miss;
+                        sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                        const double incl = scan_d((double)top);
+                        const double mtop = __shfl_sync(FULL, incl, 31);
+                        double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
+                        if (lane == 0) ex = 0.0;
+                        double rsum = (double)rest;
+    #pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
+                        total = mtop + rsum;
+                        if (__all_sync(FULL, !(total > 0.0))) {  // no transition possible (simulation.go:297 would divide by zero)
+                            dead = true;
+                            break;
+                        }
+                        const double inv = 1.0 / total;
+                        rtot = (float)inv;
+                        const double pn = ex * inv;
+                        const bool occ_me = (occu >> lane) & 1u;
+                        const uint32_t code = (ptn < (uint32_t)N) ? ptn : (ptn - (uint32_t)N + (occ_me ? 32u : 64u));
+                        pre = (top > 0.0f) ? __hiloint2double(__double2hiint(pn), (__double2loint(pn) & ~127) | (int)code) : INF;
+                        if (lane == 31) pre = mtop * inv;
+                        if (GLOG > 0) {
+                            __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
+                            if (lane == 0)
+                                __stcg(reinterpret_cast<uint4 *>(gent + 256),
+                                       make_uint4(__float_as_uint(rtot), occu, (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
+                        }
+                    }
+                    // install in the first level (without memoisation: a scratch entry that never hits; the slow path and
+                    // the replay read the total from it)
+                    sts_d(a_ent + lane * 8, pre);
+                    if (lane == 0) {
+                        sts_u2(a_ent + 256, make_uint2(__float_as_uint(rtot), K > 0 ? occu : ~occu));
+                        sts_d(a_ent + 264, total);
+                    }
+                    __syncwarp();
+                    // (read back through the same loads as the prefetch below: one register assignment for both paths)
+                    pre = lds_d(a_ent + lane * 8);
+                    tailv = lds_u2(a_ent + 256);
                 }
-                if (istar < 0) {
-                    // no mass outside the top events (rounding), or a uniform of exactly 0 (injected stream): take the
-                    // last (first) top event instead
-                    const uint32_t posu = __ballot_sync(FULL, pre < INF) & 0x7fffffffu;
-                    if (!posu) {
+
+                if (!inject) {
+                    t_part = fmaf(ek, __uint_as_float(tailv.x), t_part);
+                    if (DBG) dtd = (double)(ek * __uint_as_float(tailv.x));
+                } else {
+                    const int64_t hh = h + (int64_t)((a_rq - a_rng) >> 4) - q0;
+                    const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
+                    dtd = E.stream_e[m * total_hops + hh] / lds_d(a_ent + 264);
+                    t_acc += dtd;
+                }
+                bal = __ballot_sync(FULL, pre < u);
+                if ((int)bal > 0) {
+                    apply_top<DBG>(bal, pre, lane, N, occ, eoc, from, to);
+                } else {
+                    uint32_t occ_new;
+                    // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
+                    const uint32_t occu = __reduce_or_sync(FULL, occ);
+                    occ_new = occu;
+                    int deo = 0;
+                    // (rare enough that the sweep is simply repeated, even when this very hop already missed)
+                    if (DBG && hit) ++n_miss;
+                    sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                    const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
+                    const double total = lds_d(a_ent + 264);
+                    int istar = -1;
+                    float rf = BIGE;
+                    int skip = -1;
+                    if (bal >> 31) {
+                        const double mtopn = __shfl_sync(FULL, pre, 31);
+                        // (the uniform is re-read here rather than kept alive across the hot path's registers)
+                        double us = u;
+                        if (!inject) {
+                            const uint4 rv2 = lds_u4(a_rq);
+                            us = __hiloint2double((int)rv2.y, (int)rv2.x);
+                        }
+                        const double rres = (us - mtopn) * total;
+                        const double incl = scan_d((double)rest);
+                        double ex = __shfl_up_sync(FULL, incl, 1);
+                        if (lane == 0) ex = 0.0;
+                        const uint32_t rpos = __ballot_sync(FULL, rest > 0.0f);
+                        uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
+                        if (!b2) b2 = rpos & (0u - rpos);
+                        if (b2) {
+                            istar = 31 - __clz(b2);
+                            rf = __shfl_sync(FULL, (float)(rres - ex), istar);
+                            skip = (int)bcast_u(ptn, istar, lane);
+                        }
+                    }
+                    if (istar < 0) {
+                        // no mass outside the top events (rounding), or a uniform of exactly 0 (injected stream): take the
+                        // last (first) top event instead
+                        const uint32_t posu = __ballot_sync(FULL, pre < INF) & 0x7fffffffu;
+                        if (!posu) {
+                            dead = true;
+                            break;
+                        }
+                        istar = (bal >> 31) ? 31 - __clz(posu) : __ffs(posu) - 1;
+                    }
+                    const bool rowocc = (occu >> istar) & 1u;
+                    const float e_star = lds_f(a_mir + istar * 4);
+                    if (rowocc) {
+                        from = istar;
+                        to = -1;
+                        int lastA = -1;
+                        float sA = 0.0f;
+                        const uint32_t emp = ~occu & accm;
+                        if (emp) {  // acceptor targets: istar -> empty `lane`
+                            float rr = 0.0f;
+                            if (((emp >> lane) & 1u) && lane != skip) {
+                                const float2 v = lds_f2(a_col_me + istar * 8);
+                                rr = ma(v.x, v.y, e_me, e_star, nb);
+                            }
+                            const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+                            if (nz) {
+                                const float s = scan_f<5>(rr);
+                                const uint32_t b2 = __ballot_sync(FULL, s >= rf) & nz;
+                                if (b2) to = __ffs(b2) - 1;
+                                else {
+                                    lastA = 31 - __clz(nz);
+                                    sA = __shfl_sync(FULL, s, 31);
+                                }
+                            }
+                        }
+                        if (to < 0) {  // electrode targets: istar -> electrode `lane`
+                            float rr = 0.0f;
+                            if (lane < P && N + lane != skip)
+                                rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
+                            const int e = pick_group<5>(rr, rf - sA);
+                            to = (e >= 0) ? N + e : lastA;
+                        }
+                        if (to < 0 && skip < 0) to = (int)bcast_u(ptn, istar, lane);  // rounding fallback: the top event
+                    } else {  // empty acceptor: events electrode `lane` -> istar
+                        to = istar;
+                        float rr = 0.0f;
+                        if (lane < P && N + lane != skip)
+                            rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
+                        from = pick_group<5>(rr, rf);
+                        if (from >= 0) from += N;
+                        else if (skip < 0) from = (int)bcast_u(ptn, istar, lane);
+                    }
+                    if (__any_sync(FULL, to < 0 || from < 0)) {
                         dead = true;
                         break;
                     }
-                    istar = (bal >> 31) ? 31 - __clz(posu) : __ffs(posu) - 1;
+                    if (from < N) occ_new &= ~(1u << from);
+                    else deo -= (int)(lane == from - N);
+                    if (to < N) occ_new |= (1u << to);
+                    else deo += (int)(lane == to - N);
+                    eoc += deo;
+                occ = occ_new;
                 }
-                const bool rowocc = (occu >> istar) & 1u;
-                const float e_star = lds_f(a_mir + istar * 4);
-                if (rowocc) {
-                    from = istar;
-                    to = -1;
-                    int lastA = -1;
-                    float sA = 0.0f;
-                    const uint32_t emp = ~occu & accm;
-                    if (emp) {  // acceptor targets: istar -> empty `lane`
-                        float rr = 0.0f;
-                        if (((emp >> lane) & 1u) && lane != skip) {
-                            const float2 v = lds_f2(a_col_me + istar * 8);
-                            rr = ma(v.x, v.y, e_me, e_star, nb);
-                        }
-                        const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
-                        if (nz) {
-                            const float s = scan_f<5>(rr);
-                            const uint32_t b2 = __ballot_sync(FULL, s >= rf) & nz;
-                            if (b2) to = __ffs(b2) - 1;
-                            else {
-                                lastA = 31 - __clz(nz);
-                                sA = __shfl_sync(FULL, s, 31);
-                            }
-                        }
-                    }
-                    if (to < 0) {  // electrode targets: istar -> electrode `lane`
-                        float rr = 0.0f;
-                        if (lane < P && N + lane != skip)
-                            rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
-                        const int e = pick_group<5>(rr, rf - sA);
-                        to = (e >= 0) ? N + e : lastA;
-                    }
-                    if (to < 0 && skip < 0) to = (int)bcast_u(ptn, istar, lane);  // rounding fallback: the top event
-                } else {  // empty acceptor: events electrode `lane` -> istar
-                    to = istar;
-                    float rr = 0.0f;
-                    if (lane < P && N + lane != skip)
-                        rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
-                    from = pick_group<5>(rr, rf);
-                    if (from >= 0) from += N;
-                    else if (skip < 0) from = (int)bcast_u(ptn, istar, lane);
-                }
-                if (__any_sync(FULL, to < 0 || from < 0)) {
-                    dead = true;
-                    break;
-                }
-                if (from < N) occ_new &= ~(1u << from);
-                else deo -= (int)(lane == from - N);
-                if (to < N) occ_new |= (1u << to);
-                else deo += (int)(lane == to - N);
-                eoc += deo;
             }
 
             // ---- tallies (simulation.go:309-317: pre-hop occupation, antisymmetric traffic)
             if (DBG && h >= prehops) {
-                if ((occ >> lane) & 1u) occtime += dtd;
+                if ((occ_old >> lane) & 1u) occtime += dtd;
                 if (lane == 0) {
                     const int64_t hh = h + (int64_t)((a_rq - a_rng) >> 4) - q0;
                     if (E.traffic) {
@@ -567,12 +595,14 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                 }
             }
 
-            // ---- the new state; the energies follow from the new mask when next needed
-            occ = occ_new;
+            // ---- the new state (the energies follow from the new mask when next needed)
             if (K > 0) {  // prefetch the next state's cache line
                 const uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-                pre = lds_d(slot * ENTB + a_cache_lane);
-                tailv = lds_u2(slot * ENTB + a_cache_tail);  // rtot | key
+                uint32_t a_ent, a_pre;  // (opaque to the optimiser: one IMAD each, no rematerialised bases)
+                asm volatile("mad.lo.u32 %0, %1, 272, %2;" : "=r"(a_ent) : "r"(slot), "r"(a_cache));
+                asm volatile("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a_pre) : "r"(lane), "r"(a_ent));
+                pre = lds_d(a_pre);
+                tailv = lds_u2(a_ent + 256);  // rtot | key
             }
         }
         h = hend;
