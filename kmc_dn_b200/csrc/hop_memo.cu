@@ -49,7 +49,8 @@ namespace kmcb200 {
 #define BIGE 1.0e30f
 #define ROWB 264u  // bytes per acceptor-target row of the pair table: 33 float2
 #define ELB 132u   // bytes per electrode row of the electrode planes: 33 float
-#define ENTB 272u  // bytes per cache entry (both levels): 32 x f64 prefix | f32 1/total | u32 key | f64 total
+#define ENTB 272u  // bytes per first-level entry: 32 x f64 prefix | f32 1/total | u32 key | f64 total
+#define GENTB 288u  // second-level entry: the same + tag {launch id, member + 1} at byte 272
 
 __device__ __forceinline__ float lds_f(uint32_t a) {
     float v;
@@ -286,12 +287,13 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t accm = (1u << N) - 1u;             // N <= 31: lane 31 is never an acceptor (it holds the sentinel)
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
-    // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of ENTB bytes, same
-    // layout as the first level.  Direct-mapped with an independent hash; looked up on a first-level miss,
-    // filled together with the first level.
+    // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of GENTB bytes, the
+    // first level's layout + a tag.  Direct-mapped with an independent hash; looked up on a first-level miss,
+    // filled together with the first level.  An entry is valid only with this launch's and this member's tag, so
+    // the table is never reset.
     const int GLOG = (K > 0) ? E.gtab_log : 0;
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
-    unsigned char *gtab = (GLOG > 0) ? E.gtab + ((size_t)wslot << GLOG) * ENTB : nullptr;
+    unsigned char *gtab = (GLOG > 0) ? E.gtab + ((size_t)wslot << GLOG) * GENTB : nullptr;
 
     // ---- persistent: every warp slot pulls members from a global queue until it is empty (members differ in cost --
     //      the miss rate depends on the voltages -- so a static split would leave slots idle at the end)
@@ -307,10 +309,8 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     __syncwarp();
     if (K > 0) {  // empty caches: a key that hashes to another slot can never hit
         if (lane < K) sts_u(a_cache + lane * ENTB + 260, lane == 0 ? 1u : 0u);
-        if (GLOG > 0)
-            for (int e = lane; e < (1 << GLOG); e += 32)
-                __stcg(reinterpret_cast<unsigned int *>(gtab + (size_t)e * ENTB + 260), e == 0 ? 1u : 0u);
     }
+    const uint2 tag = make_uint2(E.launch_id, (uint32_t)m + 1u);
 
     // ---- initial state
     bool o0 = false;
@@ -413,10 +413,11 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     bool hit2 = false;
                     unsigned char *gent = nullptr;
                     if (GLOG > 0) {  // second level (global memory, L2): all loads in flight at once, one latency
-                        gent = gtab + (size_t)((occu * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * ENTB;
+                        gent = gtab + (size_t)((occu * 0x85EBCA6Bu) >> ((32 - GLOG) & 31)) * GENTB;
                         const double g_pre = __ldcg(reinterpret_cast<const double *>(gent + lane * 8));
                         const uint4 g1 = __ldcg(reinterpret_cast<const uint4 *>(gent + 256));  // rtot | key | total
-                        hit2 = __all_sync(FULL, g1.y == occu);
+                        const uint2 g2 = __ldcg(reinterpret_cast<const uint2 *>(gent + 272));  // tag
+                        hit2 = __all_sync(FULL, g1.y == occu && g2.x == tag.x && g2.y == tag.y);
                         if (hit2) {
                             pre = g_pre;
                             rtot = __uint_as_float(g1.x);
@@ -447,9 +448,11 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                         if (lane == 31) pre = mtop * inv;
                         if (GLOG > 0) {
                             __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
-                            if (lane == 0)
+                            if (lane == 0) {
                                 __stcg(reinterpret_cast<uint4 *>(gent + 256),
                                        make_uint4(__float_as_uint(rtot), occu, (uint32_t)__double2loint(total), (uint32_t)__double2hiint(total)));
+                                __stcg(reinterpret_cast<uint2 *>(gent + 272), tag);
+                            }
                         }
                     }
                     // install in the first level (without memoisation: a scratch entry that never hits; the slow path and
@@ -707,7 +710,7 @@ static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int l
 
 // logk: log2(first-level cache slots per warp); -1 disables the memoisation (same code path, every hop a miss).
 // plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the
-// second-level table E.gtab = warp_slots * 2^E.gtab_log * 272 bytes from it.
+// second-level table E.gtab = warp_slots * 2^E.gtab_log * 288 bytes from it.
 cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
     if (E.B <= 0) {
         if (plan) plan->warp_slots = 0;

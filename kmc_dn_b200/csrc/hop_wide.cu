@@ -20,8 +20,8 @@
 //     aux[32]   the lane's top event: partner (9 bits: acceptor j | 256+e hole into electrode e | 320+e hole out of
 //               electrode e), which of the lane's acceptors it starts from (3 bits), and the change it makes to the
 //               state's Zobrist hash (upper 19 bits)
-//     tail      1/total (fp32), normalised mass of the top events (fp64), total (fp64), the AS key words and a
-//               generation tag (= member index + 1: entries of earlier members can never hit)
+//     tail      1/total (fp32), normalised mass of the top events (fp64), total (fp64), the AS key words and a tag
+//               (launch id, member index + 1): entries of earlier launches / members can never hit, nothing is reset
 //
 // in a direct-mapped first level in shared memory and a second level in global memory (L2).  Unlike the reference's
 // getKey (simulation.go:29-38), which shifts all but the last 64 acceptors out of its uint64 key and therefore
@@ -47,8 +47,9 @@ namespace kmcb200 {
 #define WT_RTOT 384u   // f32 1/total
 #define WT_MTOP 392u   // f64 normalised mass of the top events
 #define WT_TOTAL 400u  // f64 total rate
-#define WT_KEY 408u    // u32 x 8 key words, then the generation tag
+#define WT_KEY 408u    // u32 x 8 key words, then the tag {member + 1, launch id}
 #define WT_GEN 440u
+#define WT_LAUNCH 444u
 
 namespace {
 
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t wb = sb + tbl_bytes + (uint32_t)warp * G::WARP_BYTES;
     const uint32_t a_mir = wb, a_rng = wb + G::MIRW * 4, a_cache = a_rng + 1024;
-    // generation tags of the first level: 0 = never written (member generations start at 1)
+    // tags of the first level: 0 = never written (member tags start at 1)
     for (int s = lane; s < (K > 0 ? K : 1); s += 32) ws_u(a_cache + s * WENT + WT_GEN, 0u);
     __syncthreads();
 
@@ -228,9 +229,10 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
         const int lo = 32 * k;
         accm[k] = (N >= lo + 32) ? ~0u : (N > lo ? ((1u << (N - lo)) - 1u) : 0u);
     }
-    // which word of the key this lane compares: lanes 0..30 the mask word (lane mod AS), lane 31 the generation tag
-    const int wl = (lane == 31) ? 99 : (lane & (AS - 1));
-    const uint32_t a_keyoff = (lane == 31) ? WT_GEN : (WT_KEY + 4u * (uint32_t)(lane & (AS - 1)));
+    // which word of the key this lane compares: lanes 0..29 the mask word (lane mod AS), lanes 30 / 31 the tag
+    // (launch id / member + 1: entries of earlier launches and members can never hit, so nothing is ever reset)
+    const int wl = (lane >= 30) ? 99 : (lane & (AS - 1));
+    const uint32_t a_keyoff = (lane == 31) ? WT_GEN : (lane == 30 ? WT_LAUNCH : (WT_KEY + 4u * (uint32_t)(lane & (AS - 1))));
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
     const int GLOG = (K > 0) ? E.gtab_log : 0;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
             occ_sw[k] = accm[k];  // energies so far: no empty site; the first sweep subtracts the empty ones
         }
         H = __reduce_xor_sync(FULL, H);
-        uint32_t occw = gen;  // lane 31 carries the generation tag in place of a mask word
+        uint32_t occw = (lane == 30) ? E.launch_id : gen;  // lanes 30 / 31 carry the tag in place of a mask word
 #pragma unroll
         for (int k = 0; k < AS; ++k)
             if (wl == k) occw = occ0[k];
@@ -712,7 +714,7 @@ static cudaError_t launch_wide_k(const LayoutDev &L, const EnsembleDev &E, int l
 }
 
 // 32 <= N <= 256 acceptors (N <= 31 runs hop_memo.cu).  logk < 0 disables the memoisation (every hop a miss).
-// plan != nullptr: only report the launch geometry; the caller sizes (and zeroes) the second-level table
+// plan != nullptr: only report the launch geometry; the caller sizes the second-level table
 // E.gtab = warp_slots * 2^E.gtab_log * 448 bytes from it.
 cudaError_t launch_wide(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
     if (E.B <= 0) {

@@ -41,8 +41,10 @@ struct EnsembleDev {
     double *prob_occupation, *prob_electrode_occ;  // MODE_PROB: fractional occupations [B,N], electrode tallies [B,P]
     double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
     unsigned long long *queue;  // memoised kernel: member work queue (zeroed before the launch)
-    unsigned char *gtab;  // memoised kernel: second-level cache, warp_slots * 2^gtab_log entries of 272 B (or null)
+    unsigned char *gtab;  // memoised kernels: second-level cache, warp_slots * 2^gtab_log entries of 288 / 448 B (or null)
     int gtab_log;         // log2(entries per warp slot); 0 = no second level
+    uint32_t launch_id;   // entries are valid only with the tag (launch_id, member + 1): the table is zeroed ONCE, at
+                          // allocation, and never reset -- neither per launch nor per member
 };
 
 // launchers (return cudaError_t of the launch)
