@@ -77,6 +77,13 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
 }
+// (volatile at the PTX level: ptxas may not merge it with an earlier identical load -- used where a value is re-read
+//  on a cold path precisely so that it need not stay in a register across the hot path)
+__device__ __forceinline__ uint4 lds_u4_again(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ double lds_d(uint32_t a) {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
@@ -160,13 +167,35 @@ __device__ __forceinline__ double energy_of(uint32_t o, uint32_t accm, double E6
     return e;
 }
 
-// Sweep: every allowed pair of the current state exactly once.  Per lane: its LARGEST rate (top, with the partner
-// site ptn) and the sum of all its other rates (rest).  Publishes the fp32 energies to the warp's mirror.
-template <int PT>
+// Running top-NR of a lane's rates: t[0] >= t[1] >= ... with their partner sites, everything else summed into rest.
+// Exact (every rate ends up in exactly one of t[] / rest); ties keep the earlier event in the higher rank.
+template <int NR>
+__device__ __forceinline__ void rank_insert(float x, int site, float (&t)[NR], int (&p)[NR], float &rest) {
+    if (NR == 1) {
+        rest += fminf(x, t[0]);
+        if (x > t[0]) p[0] = site;
+        t[0] = fmaxf(x, t[0]);
+    } else {
+        rest += fminf(x, t[NR - 1]);  // whatever drops out of the last rank (x itself if it does not make it)
+#pragma unroll
+        for (int r = NR - 1; r >= 1; --r) {
+            const bool in_above = x > t[r - 1];  // x belongs above rank r: rank r inherits rank r-1
+            const bool in_here = x > t[r];
+            p[r] = in_above ? p[r - 1] : (in_here ? site : p[r]);
+            t[r] = in_above ? t[r - 1] : fmaxf(x, t[r]);
+        }
+        if (x > t[0]) p[0] = site;
+        t[0] = fmaxf(x, t[0]);
+    }
+}
+
+// Sweep: every allowed pair of the current state exactly once.  Per lane (= acceptor): its NR LARGEST rates t[] with
+// the partner sites p[], and the sum of all its other rates (rest).  Publishes the fp32 energies to the warp's mirror.
+template <int PT, int NR>
 __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double E64, int lane, int N, int P, float nb,
                                             uint32_t a_row_me, uint32_t a_mir,
-                                            uint32_t a_elF, uint32_t a_elR, float &e_me, float &top, float &rest,
-                                            uint32_t &ptn) {
+                                            uint32_t a_elF, uint32_t a_elR, float &e_me, float (&t)[NR], int (&p)[NR],
+                                            float &rest) {
     e_me = (float)energy_of(occ, accm, E64, a_row_me);
     __syncwarp();
     sts_f(a_mir + lane * 4, e_me);
@@ -175,32 +204,27 @@ __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double 
     const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
     const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
     const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
-    top = 0.0f; rest = 0.0f; ptn = 0;
+    rest = 0.0f;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) { t[r] = 0.0f; p[r] = 0; }
     uint32_t mm = ~occ & accm;
     while (mm) {
         const int j = __ffs(mm) - 1;
         mm &= mm - 1;
         const float ej = lds_f(a_mir + j * 4);
         const float2 v = lds_f2(a_row_me + j * ROWB);
-        const float x = ma(v.x, v.y, ej, src, nb);
-        rest += fminf(x, top);
-        if (x > top) ptn = j;
-        top = fmaxf(x, top);
+        rank_insert<NR>(ma(v.x, v.y, ej, src, nb), j, t, p, rest);
     }
     if (PT > 0) {
 #pragma unroll
         for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
             const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
-            rest += fminf(x, top);
-            if (x > top) ptn = N + e;
-            top = fmaxf(x, top);
+            rank_insert<NR>(x, N + e, t, p, rest);
         }
     } else {
         for (int e = 0; e < P; ++e) {
             const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
-            rest += fminf(x, top);
-            if (x > top) ptn = N + e;
-            top = fmaxf(x, top);
+            rank_insert<NR>(x, N + e, t, p, rest);
         }
     }
 }
@@ -228,14 +252,20 @@ __device__ __forceinline__ uint32_t bit_clamp(uint32_t n) {
 }
 __device__ __forceinline__ void sts_u2(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(v.x), "r"(v.y)); }
 
-// The common case of a hop: one of the cached top events.  lane istar = the highest one whose interval starts below
-// the uniform; branch-free update (simulation.go:107-130): istar's site flips; an acceptor partner flips too; an
-// electrode partner (code >= 32: the clamped bit mask is 0) gains (32+e) or loses (64+e) one hole.
-template <bool DBG>
+// The common case of a hop: one of the cached top events.  Slot istar = the highest one whose interval starts below
+// the uniform; branch-free update (simulation.go:107-130): the slot's acceptor flips; an acceptor partner flips too;
+// an electrode partner (code >= 32: the clamped bit mask is 0) gains (32+e) or loses (64+e) one hole.
+// NR == 1: slot = acceptor.  NR > 1: the acceptor sits in bits 7..11 of the event code.
+template <bool DBG, int NR>
 __device__ __forceinline__ void apply_top(uint32_t bal, double pre, int lane, int N, uint32_t &occ, int &eoc, int &from, int &to) {
     const int istar = bfind_u(bal);
-    const uint32_t code = (uint32_t)__shfl_sync(FULL, __double2loint(pre), istar) & 127u;
-    occ ^= bit_clamp((uint32_t)istar) | bit_clamp(code);
+    const uint32_t c = (uint32_t)__shfl_sync(FULL, __double2loint(pre), istar);
+    const uint32_t code = c & 127u;
+    const uint32_t site = NR == 1 ? (uint32_t)istar : ((c >> 7) & 31u);
+    uint32_t sbit;
+    if (NR == 1) sbit = bit_clamp((uint32_t)istar);
+    else asm("bmsk.wrap.b32 %0, %1, 1;" : "=r"(sbit) : "r"(c >> 7));  // (wrap: position = low 5 bits)
+    occ ^= sbit | bit_clamp(code);
     asm("{ .reg .pred p, q; .reg .u32 t;\n"
         "  sub.u32 t, %1, %2;\n"
         "  setp.eq.u32 p, t, 32;\n"
@@ -245,13 +275,13 @@ __device__ __forceinline__ void apply_top(uint32_t bal, double pre, int lane, in
         : "+r"(eoc)
         : "r"(code), "r"(lane));
     if (DBG) {
-        if (code < 32u) { from = istar; to = (int)code; }
-        else if (code < 64u) { from = istar; to = N + (int)code - 32; }
-        else { from = N + (int)code - 64; to = istar; }
+        if (code < 32u) { from = (int)site; to = (int)code; }
+        else if (code < 64u) { from = (int)site; to = N + (int)code - 32; }
+        else { from = N + (int)code - 64; to = (int)site; }
     }
 }
 
-template <int PT, int LOGK, bool DBG>
+template <int PT, int LOGK, bool DBG, int NR>
 __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = MemoGeom<LOGK, PT>;
     constexpr int K = G::K;
@@ -285,6 +315,16 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
     const uint32_t a_elR_e = a_elR + lane * ELB;      // + istar*4    : electrode lane -> istar
     const uint32_t accm = (1u << N) - 1u;             // N <= 31: lane 31 is never an acceptor (it holds the sentinel)
+    // event slots (NR > 1): slot `lane` serves rank sl_r of acceptor sl_a; acceptor `lane` owns n_slots of its ranks
+    const int sl_a = (NR > 1 && lane < 31) ? lane % N : lane;
+    const int sl_r = (NR > 1) ? (lane < 31 ? lane / N : NR) : 0;
+    int n_slots = 1;
+    if (NR > 1) {
+        n_slots = 0;
+        if (lane < N)
+            for (int r = 0; r < NR; ++r) n_slots += (lane + r * N <= 30);
+    }
+    constexpr int CODEMASK = NR > 1 ? 4095 : 127;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
     // Second-level cache of this warp slot in global memory (L2-resident): 2^GLOG entries of GENTB bytes, the
@@ -338,8 +378,9 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     bool dead = false;
     long long n_miss = 0;
 
-    float e_me = 0.0f, top = 0.0f, rest = 0.0f;
-    uint32_t ptn = 0;
+    float e_me = 0.0f, rest = 0.0f;
+    float tk[NR];
+    int pk[NR];
 
     // Loop-carried cache line of the CURRENT state, fetched speculatively when the previous hop was applied:
     //   pre   NORMALISED exclusive fp64 prefix over the lanes' TOP rates (prefix / total rate of the state); its 7
@@ -399,9 +440,17 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
             if (__builtin_expect((int)bal > 0, 1)) {
                 t_part = fmaf(ek, __uint_as_float(tailv.x), t_part);
                 if (DBG) dtd = (double)(ek * __uint_as_float(tailv.x));
-                apply_top<DBG>(bal, pre, lane, N, occ, eoc, from, to);
+                apply_top<DBG, NR>(bal, pre, lane, N, occ, eoc, from, to);
             } else {
                 // ---- event structure of this state: cached after all, or computed and parked
+                // (the variates are re-read here rather than kept alive across the hot path's registers)
+                double u2 = u;
+                float ek2 = ek;
+                if (!inject) {
+                    const uint4 rv = lds_u4_again(a_rq);
+                    ek2 = __uint_as_float(rv.z);
+                    u2 = __hiloint2double((int)rv.y, (int)rv.x);
+                }
                 bool hit = false;
                 if (K > 0) hit = __all_sync(FULL, tailv.y == occ);
                 if (!hit) {
@@ -426,13 +475,27 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     }
                     if (!hit2) {
                         if (DBG) ++n_miss;
-                        sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
-                        const double incl = scan_d((double)top);
+                        sweep_state<PT, NR>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, tk, pk, rest);
+                        // event slots: slot s <-> rank s / N of acceptor s % N (s = 0..30; lane 31 is the sentinel)
+                        float sv = tk[0];       // this slot's rate
+                        int sp = pk[0];         // ... its partner site
+                        float rest_tot = rest;  // this ACCEPTOR's mass outside the slots
+                        if (NR > 1) {
+#pragma unroll
+                            for (int r = 1; r < NR; ++r) {
+                                const float tv = __shfl_sync(FULL, tk[r], sl_a);
+                                const int pv = __shfl_sync(FULL, pk[r], sl_a);
+                                if (sl_r == r) { sv = tv; sp = pv; }
+                                if (r >= n_slots) rest_tot += tk[r];
+                            }
+                            if (sl_r >= NR) sv = 0.0f;
+                        }
+                        const double incl = scan_d((double)sv);
                         const double mtop = __shfl_sync(FULL, incl, 31);
                         double ex = __shfl_up_sync(FULL, incl, 1);  // exact exclusive prefix
                         if (lane == 0) ex = 0.0;
-                        double rsum = (double)rest;
-    #pragma unroll
+                        double rsum = (double)rest_tot;
+#pragma unroll
                         for (int d = 16; d > 0; d >>= 1) rsum += __shfl_xor_sync(FULL, rsum, d);
                         total = mtop + rsum;
                         if (__all_sync(FULL, !(total > 0.0))) {  // no transition possible (simulation.go:297 would divide by zero)
@@ -442,9 +505,10 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                         const double inv = 1.0 / total;
                         rtot = (float)inv;
                         const double pn = ex * inv;
-                        const bool occ_me = (occu >> lane) & 1u;
-                        const uint32_t code = (ptn < (uint32_t)N) ? ptn : (ptn - (uint32_t)N + (occ_me ? 32u : 64u));
-                        pre = (top > 0.0f) ? __hiloint2double(__double2hiint(pn), (__double2loint(pn) & ~127) | (int)code) : INF;
+                        const bool occ_a = (occu >> sl_a) & 1u;
+                        uint32_t code = ((uint32_t)sp < (uint32_t)N) ? (uint32_t)sp : ((uint32_t)sp - (uint32_t)N + (occ_a ? 32u : 64u));
+                        if (NR > 1) code |= (uint32_t)sl_a << 7;
+                        pre = (sv > 0.0f) ? __hiloint2double(__double2hiint(pn), (__double2loint(pn) & ~CODEMASK) | (int)code) : INF;
                         if (lane == 31) pre = mtop * inv;
                         if (GLOG > 0) {
                             __stcg(reinterpret_cast<double *>(gent + lane * 8), pre);
@@ -469,114 +533,119 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                 }
 
                 if (!inject) {
-                    t_part = fmaf(ek, __uint_as_float(tailv.x), t_part);
-                    if (DBG) dtd = (double)(ek * __uint_as_float(tailv.x));
+                    t_part = fmaf(ek2, __uint_as_float(tailv.x), t_part);
+                    if (DBG) dtd = (double)(ek2 * __uint_as_float(tailv.x));
                 } else {
                     const int64_t hh = h + (int64_t)((a_rq - a_rng) >> 4) - q0;
                     const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
                     dtd = E.stream_e[m * total_hops + hh] / lds_d(a_ent + 264);
                     t_acc += dtd;
                 }
-                bal = __ballot_sync(FULL, pre < u);
+                bal = __ballot_sync(FULL, pre < u2);
                 if ((int)bal > 0) {
-                    apply_top<DBG>(bal, pre, lane, N, occ, eoc, from, to);
+                    apply_top<DBG, NR>(bal, pre, lane, N, occ, eoc, from, to);
                 } else {
-                    uint32_t occ_new;
-                    // ---- the rest of the list: exact two-level pick over all events EXCEPT the lanes' top ones
+                    // ---- the rest of the list: exact two-level pick over all events EXCEPT the ones that own a slot
                     const uint32_t occu = __reduce_or_sync(FULL, occ);
-                    occ_new = occu;
-                    int deo = 0;
                     // (rare enough that the sweep is simply repeated, even when this very hop already missed)
                     if (DBG && hit) ++n_miss;
-                    sweep_state<PT>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, top, rest, ptn);
+                    sweep_state<PT, NR>(occu, accm, E64, lane, N, P, nb, a_row_me, a_mir, a_elF, a_elR, e_me, tk, pk, rest);
+                    float rest_tot = rest;  // this acceptor's mass outside the slots; sk[]: its partners that own a slot
+                    int sk[NR];
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) {
+                        sk[r] = (r < n_slots && tk[r] > 0.0f) ? pk[r] : -1;
+                        if (r >= n_slots) rest_tot += tk[r];
+                    }
                     const uint32_t a_ent = a_cache + (LOGK > 0 ? ((occu * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * ENTB;
                     const double total = lds_d(a_ent + 264);
                     int istar = -1;
                     float rf = BIGE;
-                    int skip = -1;
                     if (bal >> 31) {
                         const double mtopn = __shfl_sync(FULL, pre, 31);
-                        // (the uniform is re-read here rather than kept alive across the hot path's registers)
-                        double us = u;
-                        if (!inject) {
-                            const uint4 rv2 = lds_u4(a_rq);
-                            us = __hiloint2double((int)rv2.y, (int)rv2.x);
-                        }
-                        const double rres = (us - mtopn) * total;
-                        const double incl = scan_d((double)rest);
+                        const double rres = (u2 - mtopn) * total;
+                        const double incl = scan_d((double)rest_tot);
                         double ex = __shfl_up_sync(FULL, incl, 1);
                         if (lane == 0) ex = 0.0;
-                        const uint32_t rpos = __ballot_sync(FULL, rest > 0.0f);
+                        const uint32_t rpos = __ballot_sync(FULL, rest_tot > 0.0f);
                         uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
                         if (!b2) b2 = rpos & (0u - rpos);
                         if (b2) {
                             istar = 31 - __clz(b2);
                             rf = __shfl_sync(FULL, (float)(rres - ex), istar);
-                            skip = (int)bcast_u(ptn, istar, lane);
                         }
                     }
                     if (istar < 0) {
-                        // no mass outside the top events (rounding), or a uniform of exactly 0 (injected stream): take the
-                        // last (first) top event instead
+                        // no mass outside the slots (rounding), or a uniform of exactly 0 (injected stream): take the
+                        // last (first) slot's event instead
                         const uint32_t posu = __ballot_sync(FULL, pre < INF) & 0x7fffffffu;
                         if (!posu) {
                             dead = true;
                             break;
                         }
-                        istar = (bal >> 31) ? 31 - __clz(posu) : __ffs(posu) - 1;
-                    }
-                    const bool rowocc = (occu >> istar) & 1u;
-                    const float e_star = lds_f(a_mir + istar * 4);
-                    if (rowocc) {
-                        from = istar;
-                        to = -1;
-                        int lastA = -1;
-                        float sA = 0.0f;
-                        const uint32_t emp = ~occu & accm;
-                        if (emp) {  // acceptor targets: istar -> empty `lane`
-                            float rr = 0.0f;
-                            if (((emp >> lane) & 1u) && lane != skip) {
-                                const float2 v = lds_f2(a_col_me + istar * 8);
-                                rr = ma(v.x, v.y, e_me, e_star, nb);
-                            }
-                            const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
-                            if (nz) {
-                                const float s = scan_f<5>(rr);
-                                const uint32_t b2 = __ballot_sync(FULL, s >= rf) & nz;
-                                if (b2) to = __ffs(b2) - 1;
-                                else {
-                                    lastA = 31 - __clz(nz);
-                                    sA = __shfl_sync(FULL, s, 31);
+                        const int slot = (bal >> 31) ? 31 - __clz(posu) : __ffs(posu) - 1;
+                        apply_top<DBG, NR>(1u << slot, pre, lane, N, occ, eoc, from, to);
+                    } else {
+                        uint32_t occ_new = occu;
+                        int deo = 0;
+                        int skip[NR];  // (offset by one through the unsigned OR-broadcast)
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) skip[r] = (int)bcast_u((uint32_t)(sk[r] + 1), istar, lane) - 1;
+                        const int ptop = (int)bcast_u((uint32_t)pk[0], istar, lane);  // rounding fallback: the acceptor's largest event
+                        const bool rowocc = (occu >> istar) & 1u;
+                        const float e_star = lds_f(a_mir + istar * 4);
+                        bool keepA = true, keepE = true;  // target `lane` / electrode `lane` does not own a slot
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) {
+                            keepA = keepA && lane != skip[r];
+                            keepE = keepE && N + lane != skip[r];
+                        }
+                        if (rowocc) {
+                            from = istar;
+                            to = -1;
+                            int lastA = -1;
+                            float sA = 0.0f;
+                            const uint32_t emp = ~occu & accm;
+                            if (emp) {  // acceptor targets: istar -> empty `lane`
+                                float rr = 0.0f;
+                                if (((emp >> lane) & 1u) && keepA) {
+                                    const float2 v = lds_f2(a_col_me + istar * 8);
+                                    rr = ma(v.x, v.y, e_me, e_star, nb);
+                                }
+                                const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+                                if (nz) {
+                                    const float s = scan_f<5>(rr);
+                                    const uint32_t b2 = __ballot_sync(FULL, s >= rf) & nz;
+                                    if (b2) to = __ffs(b2) - 1;
+                                    else {
+                                        lastA = 31 - __clz(nz);
+                                        sA = __shfl_sync(FULL, s, 31);
+                                    }
                                 }
                             }
-                        }
-                        if (to < 0) {  // electrode targets: istar -> electrode `lane`
+                            if (to < 0) {  // electrode targets: istar -> electrode `lane`
+                                float rr = 0.0f;
+                                if (lane < P && keepE)
+                                    rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
+                                const int e = pick_group<5>(rr, rf - sA);
+                                to = (e >= 0) ? N + e : lastA;
+                            }
+                            if (to < 0) to = ptop;
+                        } else {  // empty acceptor: events electrode `lane` -> istar
+                            to = istar;
                             float rr = 0.0f;
-                            if (lane < P && N + lane != skip)
-                                rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
-                            const int e = pick_group<5>(rr, rf - sA);
-                            to = (e >= 0) ? N + e : lastA;
+                            if (lane < P && keepE)
+                                rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
+                            from = pick_group<5>(rr, rf);
+                            from = (from >= 0) ? from + N : ptop;
                         }
-                        if (to < 0 && skip < 0) to = (int)bcast_u(ptn, istar, lane);  // rounding fallback: the top event
-                    } else {  // empty acceptor: events electrode `lane` -> istar
-                        to = istar;
-                        float rr = 0.0f;
-                        if (lane < P && N + lane != skip)
-                            rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
-                        from = pick_group<5>(rr, rf);
-                        if (from >= 0) from += N;
-                        else if (skip < 0) from = (int)bcast_u(ptn, istar, lane);
+                        if (from < N) occ_new &= ~(1u << from);
+                        else deo -= (int)(lane == from - N);
+                        if (to < N) occ_new |= (1u << to);
+                        else deo += (int)(lane == to - N);
+                        eoc += deo;
+                        occ = occ_new;
                     }
-                    if (__any_sync(FULL, to < 0 || from < 0)) {
-                        dead = true;
-                        break;
-                    }
-                    if (from < N) occ_new &= ~(1u << from);
-                    else deo -= (int)(lane == from - N);
-                    if (to < N) occ_new |= (1u << to);
-                    else deo += (int)(lane == to - N);
-                    eoc += deo;
-                occ = occ_new;
                 }
             }
 
@@ -677,7 +746,11 @@ static cudaError_t launch_memo_t(const LayoutDev &L, const EnsembleDev &E, cudaS
     int warps = 8;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
-    auto kern = dbg ? kmc_memo_kernel<PT, LOGK, true> : kmc_memo_kernel<PT, LOGK, false>;
+    // ranked events per acceptor: as many as the 31 slots hold (3 for N <= 10, 2 up to N = 24, else 1)
+    const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
+    auto kern = nr == 3 ? (dbg ? kmc_memo_kernel<PT, LOGK, true, 3> : kmc_memo_kernel<PT, LOGK, false, 3>)
+              : nr == 2 ? (dbg ? kmc_memo_kernel<PT, LOGK, true, 2> : kmc_memo_kernel<PT, LOGK, false, 2>)
+                        : (dbg ? kmc_memo_kernel<PT, LOGK, true, 1> : kmc_memo_kernel<PT, LOGK, false, 1>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     // persistent CTAs: as many as stay resident; every warp slot loops over its members
@@ -702,8 +775,6 @@ template <int PT>
 static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
     switch (logk) {
         case -1: return launch_memo_t<PT, -1>(L, E, st, launches, plan);
-        case 3: return launch_memo_t<PT, 3>(L, E, st, launches, plan);
-        case 5: return launch_memo_t<PT, 5>(L, E, st, launches, plan);
         default: return launch_memo_t<PT, 4>(L, E, st, launches, plan);
     }
 }

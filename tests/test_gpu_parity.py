@@ -304,6 +304,7 @@ def test_state_memoisation_is_transparent(golden_py, fixtures_subset):
     (KMCB200_FLAG_NO_MEMO) every trajectory is bit-identical -- hop sequence, time, tallies, occupation --
     and the cache really is used (rate structures evaluated on a small fraction of the hops)."""
     cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
+             "c2_grid_N16_P8": golden_py["c2_grid_N16_P8"],  # two ranked events per acceptor (three for N <= 10)
              "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"], "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"]),
              # hop_wide.cu: multi-word masks, 1 / 2 / 4 / 8 acceptors per lane
              "N32_P8": synthetic_layout(32, 8, 4), "N48_P8": synthetic_layout(48, 8, 1),
