@@ -50,6 +50,7 @@ namespace kmcb200 {
 #define WT_KEY 408u    // u32 x 8 key words, then the tag {member + 1, launch id}
 #define WT_GEN 440u
 #define WT_LAUNCH 444u
+#define RING_D 4       // rows in flight per warp in the cp.async ring of the GT sweep
 
 namespace {
 
@@ -130,7 +131,7 @@ struct SweepOut {
 template <int AS, bool GT>
 __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, int P, int lane, float nb, const uint32_t (&accm)[AS],
                                            const uint32_t (&occ)[AS], uint32_t (&occ_sw)[AS], double (&eps64)[AS],
-                                           uint32_t a_mir, SweepOut<AS> &o) {
+                                           uint32_t a_mir, uint32_t a_ring, SweepOut<AS> &o) {
     // ---- energies: flip the sites that differ (simulation.go:107-130, applied exactly)
 #pragma unroll
     for (int kw = 0; kw < AS; ++kw) {
@@ -162,6 +163,72 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
         o.top[k] = 0.0f; o.rest[k] = 0.0f; o.ptn[k] = 0;
     }
     __syncwarp();
+    if (GT) {
+        // The pair table lives in global memory (L2): the rows of the state's targets -- its empty acceptors, then the
+        // electrodes -- are streamed through a per-warp ring in shared memory with cp.async, RING_D rows ahead of the
+        // arithmetic.  Every lane copies exactly the elements it consumes itself (columns lane + 32k), so
+        // cp.async.wait_group is all the synchronisation there is.
+        const uint32_t a_list = a_ring + RING_D * AS * 256;  // u16 row indices: empties in ascending order, then N + e
+        int n_emp = 0;
+#pragma unroll
+        for (int kw = 0; kw < AS; ++kw) {
+            const uint32_t w = ~occ[kw] & accm[kw];
+            if ((w >> lane) & 1u) {
+                const int pos = n_emp + __popc(w & ((1u << lane) - 1u));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_list + 2u * (uint32_t)pos), "h"((unsigned short)(kw * 32 + lane)));
+            }
+            n_emp += __popc(w);
+        }
+        if (lane < P) asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_list + 2u * (uint32_t)(n_emp + lane)), "h"((unsigned short)(N + lane)));
+        __syncwarp();
+        const int T = n_emp + P;
+        auto issue = [&](int t) {
+            if (t < T) {
+                unsigned short jr;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(jr) : "r"(a_list + 2u * (uint32_t)t));
+                const float2 *row = tbl + (int)jr * PITCH + lane;
+                const uint32_t dst = a_ring + (uint32_t)(t % RING_D) * (AS * 256) + lane * 8u;
+#pragma unroll
+                for (int k = 0; k < AS; ++k)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + k * 256u), "l"(row + 32 * k));
+            }
+            asm volatile("cp.async.commit_group;");
+        };
+#pragma unroll
+        for (int t = 0; t < RING_D; ++t) issue(t);
+        for (int t = 0; t < T; ++t) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(RING_D - 1));
+            unsigned short jr;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(jr) : "r"(a_list + 2u * (uint32_t)t));
+            const int j = (int)jr;
+            const uint32_t srcb = a_ring + (uint32_t)(t % RING_D) * (AS * 256) + lane * 8u;
+            const float sj = wl_f(a_mir + (j < N ? j : 32 * AS + (j - N)) * 4);
+            float2 v[AS];
+#pragma unroll
+            for (int k = 0; k < AS; ++k)
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[k].x), "=f"(v[k].y) : "r"(srcb + k * 256u));
+            if (t < n_emp) {  // acceptor target j: lane's occupied acceptors -> j
+#pragma unroll
+                for (int k = 0; k < AS; ++k) {
+                    const float x = ma_rate(v[k], sj, src[k], nb);
+                    o.rest[k] += fminf(x, o.top[k]);
+                    if (x > o.top[k]) o.ptn[k] = j;
+                    o.top[k] = fmaxf(x, o.top[k]);
+                }
+            } else {  // electrode j - N: acceptor -> electrode if occupied, electrode -> acceptor if empty
+#pragma unroll
+                for (int k = 0; k < AS; ++k) {
+                    const float tc = (nbs[k] == nb) ? v[k].x : v[k].y;
+                    const float x = tc * ex2_approx(fminf((sj - o.s_true[k]) * nbs[k], 0.0f));
+                    o.rest[k] += fminf(x, o.top[k]);
+                    if (x > o.top[k]) o.ptn[k] = j;
+                    o.top[k] = fmaxf(x, o.top[k]);
+                }
+            }
+            issue(t + RING_D);
+        }
+        asm volatile("cp.async.wait_group 0;");
+    } else {
 #pragma unroll
     for (int kw = 0; kw < AS; ++kw) {
         uint32_t mm = ~occ[kw] & accm[kw];
@@ -189,20 +256,22 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
             o.top[k] = fmaxf(x, o.top[k]);
         }
     }
+    }
 }
 
 }  // namespace
 
-template <int AS, int LOGK>
+template <int AS, int LOGK, bool GT>
 struct WideGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
     static constexpr int MIRW = 32 * AS + 32;  // per-warp mirror: acceptor energies [0,32*AS), electrode energies after
-    static constexpr int WARP_BYTES = MIRW * 4 + 1024 + (K > 0 ? K : 1) * (int)WENT;  // mirror | variates | entries
+    static constexpr int RINGB = GT ? RING_D * AS * 256 + 2 * (32 * AS + 32) : 0;  // row ring + row-index list
+    static constexpr int WARP_BYTES = MIRW * 4 + 1024 + (K > 0 ? K : 1) * (int)WENT + RINGB;  // mirror | variates | entries | ring
 };
 
 template <int AS, int LOGK, bool DBG, bool GT>
 __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const EnsembleDev E) {
-    using G = WideGeom<AS, LOGK>;
+    using G = WideGeom<AS, LOGK, GT>;
     constexpr int K = G::K;
     constexpr int PITCH = 32 * AS + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -219,6 +288,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t wb = sb + tbl_bytes + (uint32_t)warp * G::WARP_BYTES;
     const uint32_t a_mir = wb, a_rng = wb + G::MIRW * 4, a_cache = a_rng + 1024;
+    const uint32_t a_ring = a_cache + (K > 0 ? K : 1) * WENT;
     // tags of the first level: 0 = never written (member tags start at 1)
     for (int s = lane; s < (K > 0 ? K : 1); s += 32) ws_u(a_cache + s * WENT + WT_GEN, 0u);
     __syncthreads();
@@ -355,7 +425,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
                     if (!hit2) {
                         if (DBG) ++n_miss;
                         SweepOut<AS> sw;
-                        wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, sw);
+                        wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sw);
                         // the lane's top event and everything else
                         int ktop = 0;
                         float top = sw.top[0];
@@ -477,7 +547,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
                     const uint32_t a_ent = a_cache + (LOGK > 0 ? (Hu >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * WENT;
                     if (DBG && hit) ++n_miss;
                     SweepOut<AS> sw;
-                    wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, sw);
+                    wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sw);
                     const double total = wl_d(a_ent + WT_TOTAL);
                     int ktop = 0;
                     {
@@ -662,7 +732,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
             for (int k = 0; k < AS; ++k) occ[k] = __reduce_or_sync(FULL, lane == k ? occw : 0u);
             if (E.site_energies_out) {  // energies of the final mask
                 SweepOut<AS> sw;
-                wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, sw);
+                wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sw);
             }
 #pragma unroll
             for (int k = 0; k < AS; ++k) {
@@ -682,7 +752,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
 
 template <int AS, int LOGK, bool GT>
 static cudaError_t launch_wide_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
-    using G = WideGeom<AS, LOGK>;
+    using G = WideGeom<AS, LOGK, GT>;
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e || E.misses;
     int warps = 4;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
