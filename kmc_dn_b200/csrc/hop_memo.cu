@@ -266,20 +266,30 @@ __device__ __forceinline__ void apply_top(uint32_t bal, double pre, int lane, in
     if (NR == 1) sbit = bit_clamp((uint32_t)istar);
     else asm("bmsk.wrap.b32 %0, %1, 1;" : "=r"(sbit) : "r"(c >> 7));  // (wrap: position = low 5 bits)
     occ ^= sbit | bit_clamp(code);
-    asm("{ .reg .pred p, q; .reg .u32 t;\n"
-        "  sub.u32 t, %1, %2;\n"
-        "  setp.eq.u32 p, t, 32;\n"
-        "  setp.eq.u32 q, t, 64;\n"
+    asm("{ .reg .pred p, q;\n"
+        "  setp.eq.u32 p, %1, %2;\n"
+        "  setp.eq.u32 q, %1, %3;\n"
         "  @p add.s32 %0, %0, 1;\n"
         "  @q add.s32 %0, %0, -1; }"
         : "+r"(eoc)
-        : "r"(code), "r"(lane));
+        : "r"(code), "r"(lane + 32), "r"(lane + 64));
     if (DBG) {
         if (code < 32u) { from = (int)site; to = (int)code; }
         else if (code < 64u) { from = (int)site; to = N + (int)code - 32; }
         else { from = N + (int)code - 64; to = (int)site; }
     }
 }
+
+// Speculative fetch of the cache line of the state just entered (multiplicative hash -> first-level slot).
+#define PREFETCH_LINE()                                                                                          \
+    do {                                                                                                         \
+        const uint32_t slot_ = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;            \
+        uint32_t a_ent_, a_pre_; /* (opaque to the optimiser: one IMAD each, no rematerialised bases) */         \
+        asm volatile("mad.lo.u32 %0, %1, 272, %2;" : "=r"(a_ent_) : "r"(slot_), "r"(a_cache_op));                \
+        asm volatile("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a_pre_) : "r"(lane), "r"(a_ent_));                       \
+        pre = lds_d(a_pre_);                                                                                     \
+        tailv = lds_u2(a_ent_ + 256); /* rtot | key */                                                           \
+    } while (0)
 
 template <int PT, int LOGK, bool DBG, int NR>
 __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, const EnsembleDev E) {
@@ -315,6 +325,12 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
     const uint32_t a_elR_e = a_elR + lane * ELB;      // + istar*4    : electrode lane -> istar
     const uint32_t accm = (1u << N) - 1u;             // N <= 31: lane 31 is never an acceptor (it holds the sentinel)
+    // the cache base as an OPAQUE register value (round trip through shared memory): otherwise ptxas re-derives it
+    // from the warp base inside the hop loop and spends an extra IMAD per hop on a second entry address
+    sts_u(a_mir + 124, a_cache);
+    __syncwarp();
+    const uint32_t a_cache_op = lds_u(a_mir + 124);
+    __syncwarp();
     // event slots (NR > 1): slot `lane` serves rank sl_r of acceptor sl_a; acceptor `lane` owns n_slots of its ranks
     const int sl_a = (NR > 1 && lane < 31) ? lane % N : lane;
     const int sl_r = (NR > 1) ? (lane < 31 ? lane / N : NR) : 0;
@@ -668,14 +684,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
             }
 
             // ---- the new state (the energies follow from the new mask when next needed)
-            if (K > 0) {  // prefetch the next state's cache line
-                const uint32_t slot = LOGK > 0 ? ((occ * 0x9E3779B1u) >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u;
-                uint32_t a_ent, a_pre;  // (opaque to the optimiser: one IMAD each, no rematerialised bases)
-                asm volatile("mad.lo.u32 %0, %1, 272, %2;" : "=r"(a_ent) : "r"(slot), "r"(a_cache));
-                asm volatile("mad.lo.u32 %0, %1, 8, %2;" : "=r"(a_pre) : "r"(lane), "r"(a_ent));
-                pre = lds_d(a_pre);
-                tailv = lds_u2(a_ent + 256);  // rtot | key
-            }
+            if (K > 0) PREFETCH_LINE();
         }
         h = hend;
         if (h == prehops && prehops > 0 && !dead) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
