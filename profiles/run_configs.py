@@ -57,6 +57,8 @@ def cpu_rate(w, seconds, semantics="go", use_cache=True, scale=1.0):
                                occupation0=w["occupation0"], seed0=1)
         return B * h / (time.perf_counter() - t0)
 
+    if len(w["V"]) == 1:  # single-trajectory latency: one member on one core
+        return run(1, hops), 1, hops
     r0 = run(2 * n, max(1, min(hops, 500)))
     B = int(max(n, min(len(w["V"]), r0 * seconds // hops // n * n)))
     if B * hops > r0 * seconds * 4:  # a single member is already too long: shorten the trajectories instead
@@ -76,6 +78,7 @@ def main():
     from kmc_dn_b200 import workloads
     q = args.quick
     configs = [
+        ("C1-single", workloads.c1_basic(B=1), 1.0),   # single-trajectory latency
         ("C1", workloads.c1_basic(B=4096), 1.0),
         ("C2", workloads.c2_grid4x4(seeds=64), 1.0),
         ("C3", workloads.c3_voltage_search(n_controls=1024 if q else 16384, seeds=16, hops=10000), 1.0),
