@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                     }
                     // install in the first level (without memoisation: a scratch entry that never hits; the slow path and
                     // the replay read the total from it)
+                    __syncwarp();  // (the other lanes' prefetch reads of this slot are ordered before lane 0's writes)
                     sts_d(a_ent + lane * 8, pre);
                     if (lane == 0) {
                         sts_u2(a_ent + 256, make_uint2(__float_as_uint(rtot), K > 0 ? occu : ~occu));

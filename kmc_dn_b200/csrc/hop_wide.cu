@@ -474,6 +474,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
                         }
                     }
                     // install in the first level (without memoisation: a scratch entry that never hits)
+                    __syncwarp();  // (the other lanes' prefetch reads of this slot are ordered before lane 0's writes)
                     ws_d(a_ent + lane * 8, pre);
                     ws_u(a_ent + 256 + lane * 4, aux);
                     ws_u(a_ent + a_keyoff, K > 0 ? occw : ~occw);

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Small invocations of every production kernel variant, meant to be run under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python profiles/sanitizer_run.py
+    compute-sanitizer --tool racecheck python profiles/sanitizer_run.py
+
+Covers hop_memo.cu (1 / 2 / 3 ranked events per acceptor, cache on / off, record + trace instantiation, second-level
+table) and hop_wide.cu (1 / 2 / 4 / 8 acceptors per lane, shared-memory and cp.async-ring sweeps, cache on / off)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+from kmc_dn_b200.ensemble import Layout  # noqa: E402
+from tests.util import synthetic_layout  # noqa: E402
+
+
+def main():
+    cases = [(5, 3), (10, 2), (16, 8), (30, 8), (31, 1), (32, 8), (48, 8), (100, 5), (256, 8)]
+    for N, P in cases:
+        c = synthetic_layout(N, P, 11 + N, fill=0.85)
+        lay = Layout(c["N"], c["P"], c["distances"], c["transitions_constant"], nu=c["nu"], I_0=c["I_0"], R=c["R"])
+        B = 6
+        hops = 400 if N <= 64 else 120
+        V = np.tile(c["electrode_v"], (B, 1)) + np.arange(B)[:, None]
+        E = np.tile(c["E_constant"], (B, 1))
+        kw = dict(E_constant=E, occupation0=c["occupation"], seed=3)
+        a = lay.run(hops, c["kT"], V, memo=True, **kw)
+        b = lay.run(hops, c["kT"], V, memo=False, **kw)
+        assert np.array_equal(a["time"], b["time"]) and np.array_equal(a["electrode_occupation"], b["electrode_occupation"])
+        r = lay.run(hops, c["kT"], V[:2], E_constant=E[:2], occupation0=c["occupation"], seed=4, prehops=50, record=True,
+                    trace=True, want_occupation=True, want_site_energies=True, want_misses=True)
+        assert np.isfinite(r["time"]).all()
+        lay.close()
+        print(f"N={N} P={P}: ok", flush=True)
+
+
+if __name__ == "__main__":
+    main()
