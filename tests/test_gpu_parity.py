@@ -348,6 +348,52 @@ def test_wide_memo_kernel_agrees_with_general_kernel(monkeypatch):
     assert za < 4.5 and (z < 4.5).all(), (za, z)
 
 
+def test_random_layouts_memoisation_and_trace_consistency():
+    """40 random layouts (N = 1..70, P = 0..9, random filling / temperature / interaction strength): memoised and
+    unmemoised runs are bit-identical, every traced hop is allowed, tallies follow from the trace."""
+    rng = np.random.default_rng(2026)
+    for it in range(40):
+        N = int(rng.choice([1, 2, 3, 7, 10, 11, 15, 16, 17, 24, 25, 30, 31, 32, 33, 40, 64, 65, 70]))
+        P = int(rng.integers(0, 10))
+        if P == 0 and N < 2:
+            P = 1
+        c = synthetic_layout(N, P, 100 + it, kT=float(rng.choice([0.5, 1.0, 4.0])), I_0=float(rng.choice([0.0, 30.0, 100.0])),
+                             fill=float(rng.uniform(0.1, 0.9)))
+        if P == 0 and (c["occupation"].all() or not c["occupation"].any()):
+            c["occupation"][0] = not c["occupation"][0]
+        B, hops = 3, 1500
+        V = np.tile(c["electrode_v"], (B, 1)) + rng.normal(0, 5, (B, P))
+        E = np.tile(c["E_constant"], (B, 1))
+        lay = _layout(c)
+        kw = dict(E_constant=E, occupation0=c["occupation"], seed=it, trace=True, want_occupation=True, record=True)
+        a = lay.run(hops, c["kT"], V, memo=True, **kw)
+        b = lay.run(hops, c["kT"], V, memo=False, **kw)
+        lay.close()
+        tag = (it, N, P)
+        np.testing.assert_array_equal(a["trace"], b["trace"], err_msg=str(tag))
+        np.testing.assert_array_equal(a["time"], b["time"], err_msg=str(tag))
+        np.testing.assert_array_equal(a["avg_occupation"], b["avg_occupation"], err_msg=str(tag))
+        for m in range(B):
+            if not np.isfinite(a["time"][m]):
+                continue  # dead state reached (closed system that ran out of moves)
+            occ = c["occupation"].copy()
+            eo = np.zeros(P, dtype=np.int64)
+            for f, t in a["trace"][m]:
+                assert f != t and not (f >= N and t >= N), tag
+                if f < N:
+                    assert occ[f], tag
+                    occ[f] = False
+                else:
+                    eo[f - N] -= 1
+                if t < N:
+                    assert not occ[t], tag
+                    occ[t] = True
+                else:
+                    eo[t - N] += 1
+            np.testing.assert_array_equal(a["occupation"][m].astype(bool), occ, err_msg=str(tag))
+            np.testing.assert_array_equal(a["electrode_occupation"][m], eo, err_msg=str(tag))
+
+
 def test_superposition_matvec_equals_explicit_E_constant(fixtures_subset):
     """E_constant[m,:] = basis[P,:] + V[m,:] @ basis[:P,:] on device == passing E_constant explicitly."""
     f = fixtures_subset["XOR_wide/test0"]
