@@ -38,21 +38,36 @@ def parse():
     ap.add_argument("--seeds", type=int, default=16)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 = BASELINE.json's metric config (default); c5 = examples/scaling.py, 8192 members of a 256-acceptor "
+                         "layout sharded over the GPUs (strong scaling), 1e4 hops")
     return ap.parse_args()
 
 
 def workload(args):
     from kmc_dn_b200 import workloads
+    if args.workload == "c5":
+        w = workloads.c5_scaling()
+        w["hops"] = args.hops
+        return w
     return workloads.c3_voltage_search(n_controls=args.controls, seeds=args.seeds, hops=args.hops)
 
 
 def config_of(args, w, n_gpus):
+    lt = w["tables"]
+    common = {"hops_per_member": int(args.hops), "N": int(lt.N), "P": int(lt.P),
+              "l2": "flushed between timed steps (256 MiB write)", "rng": "Philox4x32-10 (seed, global member index)"}
+    if args.workload == "c5":
+        return {"workload": "C5 examples/scaling.py: uniform-random layout, 256 acceptors, 25 donors, 8 electrodes, "
+                            f"{len(w['V'])} members with U(-150,150) voltages in total, {args.hops} hops per member per step",
+                "members_total": int(len(w["V"])),
+                "parallelism": f"ensemble-sharded x{n_gpus}, strong scaling (no data-path collective; final NCCL all_gather "
+                               "of tallies)", **common}
     return {"workload": "C3 boolean_logic/voltage_search: reference layout 0 (30 acceptors, 3 donors), 8 electrodes, "
                         f"{args.controls} control vectors x 4 inputs x {args.seeds} seeds = {len(w['V'])} members per GPU, "
                         f"{args.hops} hops per member per step",
-            "members_per_gpu": int(len(w["V"])), "hops_per_member": int(args.hops), "N": 30, "P": 8,
-            "parallelism": f"ensemble-sharded x{n_gpus} (no data-path collective; final NCCL all_gather of tallies)",
-            "l2": "flushed between timed steps (256 MiB write)", "rng": "Philox4x32-10 (seed, global member index)"}
+            "members_per_gpu": int(len(w["V"])),
+            "parallelism": f"ensemble-sharded x{n_gpus} (no data-path collective; final NCCL all_gather of tallies)", **common}
 
 
 # ---------------------------------------------------------------------------------------- CPU arms
@@ -174,10 +189,20 @@ def main():
 
     w = workload(args)
     lt = w["tables"]
+    strong = args.workload == "c5"
+    if strong:  # a fixed ensemble, contiguous blocks of members per rank (kmc_dn_b200/sharding.py)
+        from kmc_dn_b200.sharding import shard_bounds
+        B_total = len(w["V"])
+        lo, hi = shard_bounds(B_total, world, rank)
+        w["V"], w["kT"] = w["V"][lo:hi], w["kT"][lo:hi]
+        member0 = lo
     B = len(w["V"])
+    if strong:
+        assert B * world == B_total, "strong-scaling workload: the member count must divide by the number of GPUs"
     hops = args.hops
     lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R, device=local)
-    member0 = rank * B  # global numbering: every rank holds a full C3 ensemble with its own Philox streams
+    if not strong:
+        member0 = rank * B  # global numbering: every rank holds a full C3 ensemble with its own Philox streams
 
     # ---- device-resident inputs (value leg) and pinned host buffers (e2e leg)
     V_h = torch.from_numpy(np.ascontiguousarray(w["V"])).pin_memory()
@@ -251,7 +276,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, e2e_ms = float(t[0]), float(t[1])
-    hops_per_step_all = float(B) * hops * world
+    hops_per_step_all = (float(B_total) if strong else float(B) * world) * hops
     value = hops_per_step_all * args.steps / (ms * 1e-3)
     e2e_value = hops_per_step_all * args.steps / (e2e_ms * 1e-3)
     h2d = V_h.numel() * 8 + kT_h.numel() * 8 + occ_h.numel() + basis_h.numel() * 8
@@ -259,13 +284,15 @@ def main():
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+                "vs_baseline": None,
                 "dtype": "f32 rates / f64 cumulative+time", "data": "synthetic", "config": config_of(args, w, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall}
         stats = sample_statistics(lay, w, lt, member0)
-        line["roofline"] = roofline(value / world, ms / args.steps, B, hops, lt, stats, lay, local)
+        line["roofline"] = roofline(value / world, ms / args.steps, B, hops, lt, stats, lay, local,
+                                    "wide" if lt.N > 31 else "memo")
         if world == 1 and not args.no_cpu_baseline:
             s = cpu_sample(w, args.cpu_seconds)
             s_nc = cpu_sample(w, args.cpu_seconds / 3, use_cache=False)
@@ -300,6 +327,7 @@ def lay_run_host(lay, B, hops, kT, V, basis, occ0, time_out, eo_out, seed, membe
 def sample_statistics(lay, w, lt, member0, n_sample=4096):
     """One small DBG launch on a strided subset of the ensemble: cache hit rate and mean hole count, from which the
     algorithmic pair count A = n_h*(N-n_h) + N*P of SURVEY.md 8(d) follows."""
+    n_sample = min(n_sample, len(w["V"]))
     idx = np.linspace(0, len(w["V"]) - 1, n_sample).astype(np.int64)
     r = lay.run(w["hops"], w["kT"][idx], w["V"][idx], basis=lt.basis, occupation0=w["occupation0"], seed=7,
                 member_index0=member0, record=True, want_misses=True)
@@ -309,7 +337,7 @@ def sample_statistics(lay, w, lt, member0, n_sample=4096):
             "pairs_per_hop_A": A, "pairs_per_hop_A_nominal": lt.N * (lt.N - 1) + 2 * lt.N * lt.P}
 
 
-def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device):
+def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device, kernel="memo"):
     """the hop loop is bounded by instruction issue, the XU pipe (MUFU.EX2) and shared memory --
     not by HBM or tensor cores.  The memoised kernel is ISSUE-bound, so the headline fraction is issue-slot
     utilisation: warp-instructions per second (hops/s measured here x warp-instructions per hop from the committed
@@ -331,11 +359,11 @@ def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bytes_per_member = 8 * lt.P + 8 + lt.N + 8 + 8 * lt.P
     hbm_achieved = B * bytes_per_member / (ms_per_step * 1e-3) / 1e9
-    prof = os.path.join(ROOT, "profiles", "ncu_r01_memo_kernel.json")
+    prof = os.path.join(ROOT, "profiles", f"ncu_r01_{kernel}_kernel.json")
     ncu = json.load(open(prof)) if os.path.exists(prof) else {}
     wih = ncu.get("warp_inst_per_hop")
     achieved = hops_per_s_gpu * wih if wih else None
-    return {"bound": "issue", "kernel": "kmc_memo_kernel", "achieved": achieved / 1e9 if achieved else None,
+    return {"bound": "issue", "kernel": f"kmc_{kernel}_kernel", "achieved": achieved / 1e9 if achieved else None,
             "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s", "frac": achieved / issue_peak if achieved else None,
             "peak_source": "dependent-free IADD micro-kernel on this device (kmcb200_measure_peak); nominal 148 SM x 4/clk",
             "work_per_hop": {"warp_inst": wih, "ncu_issue_active_pct": ncu.get("issue_active_pct"), "source": ncu.get("source"),
