@@ -317,19 +317,30 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             MemoPlan plan{0};
             le = narrow ? launch_memo(D, E, logk, st, nullptr, &plan) : launch_wide(D, E, logk, st, nullptr, &plan);
             if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-            const size_t bytes = ((size_t)plan.warp_slots << glog) * (narrow ? 288 : 448);
+            const size_t entry = narrow ? 288 : 448;
+            size_t bytes = ((size_t)plan.warp_slots << glog) * entry;
             if (bytes > lay->gtab_bytes) {
                 if (lay->gtab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->gtab)); lay->gtab = nullptr; lay->gtab_bytes = 0; }
-                CU(cudaMalloc(&lay->gtab, bytes));
-                lay->gtab_bytes = bytes;
-                CU(cudaMemsetAsync(lay->gtab, 0, bytes, st));  // once: tags (0, 0) never match (launch ids start at 1)
-                lay->launch_id = 0;
+                // the table is a cache: if the device is short of memory, halve it until it fits (or do without)
+                while (glog > 0 && cudaMalloc(&lay->gtab, bytes) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    lay->gtab = nullptr;
+                    --glog;
+                    bytes >>= 1;
+                }
+                if (glog > 0) {
+                    lay->gtab_bytes = bytes;
+                    CU(cudaMemsetAsync(lay->gtab, 0, bytes, st));  // once: tags (0, 0) never match (launch ids start at 1)
+                    lay->launch_id = 0;
+                }
             }
-            if (++lay->launch_id == 0) {  // 2^32 launches on one layout: start the tags over
-                CU(cudaMemsetAsync(lay->gtab, 0, lay->gtab_bytes, st));
-                lay->launch_id = 1;
+            if (glog > 0) {
+                if (++lay->launch_id == 0) {  // 2^32 launches on one layout: start the tags over
+                    CU(cudaMemsetAsync(lay->gtab, 0, lay->gtab_bytes, st));
+                    lay->launch_id = 1;
+                }
+                E.gtab = (unsigned char *)lay->gtab; E.gtab_log = glog; E.launch_id = lay->launch_id;
             }
-            E.gtab = (unsigned char *)lay->gtab; E.gtab_log = glog; E.launch_id = lay->launch_id;
         }
         if (!lay->queue) CU(cudaMalloc((void **)&lay->queue, 256));
         CU(cudaMemsetAsync(lay->queue, 0, 256, st));
