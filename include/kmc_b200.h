@@ -181,6 +181,13 @@ void kmcb200_layout_destroy(kmcb200_layout *layout);
  * (message via kmcb200_last_error).  Host-pointer calls are synchronous. */
 int kmcb200_run_ensemble(kmcb200_layout *layout, const kmcb200_ensemble_args *args);
 
+/* The same call spread over several GPUs of one box from ONE process (the ensemble shards
+ * trivially; the reference's counterpart is the goroutine fan-out of parallelSimulations,
+ * simulationWrapper.go:280-314): `layouts` are n_layouts copies of one layout created on different devices; the
+ * members are cut into contiguous blocks, one host thread per device.  Host pointers only, stream must be NULL.
+ * Results are identical to a single-device call (streams are numbered by global member index). */
+int kmcb200_run_ensemble_multi(kmcb200_layout *const *layouts, int n_layouts, const kmcb200_ensemble_args *args);
+
 /* fp32 energies + dense rate matrix of ONE given state with the FAST kernel's arithmetic
  * (parity probe for the 1e-6-relative checks).  All host pointers.  site_energies_io[S]:
  * if energies_given != 0 the rates are evaluated AT these energies, otherwise the kernel's own

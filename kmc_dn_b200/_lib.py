@@ -44,6 +44,7 @@ EXPORTS = ["wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlu
            "wrapperSimulateProbability",
            "parallelSimulations", "kmcb200_device_count", "kmcb200_last_error", "kmcb200_version",
            "kmcb200_set_seed", "kmcb200_layout_create", "kmcb200_layout_destroy", "kmcb200_run_ensemble",
+           "kmcb200_run_ensemble_multi",
            "kmcb200_probe_rates", "kmcb200_launch_count", "kmcb200_sizeof_ensemble_args", "kmcb200_measure_peak"]
 
 _lib = None
@@ -74,6 +75,8 @@ def load():
     lib.kmcb200_layout_destroy.argtypes = [C.c_void_p]
     lib.kmcb200_run_ensemble.argtypes = [C.c_void_p, C.POINTER(EnsembleArgs)]
     lib.kmcb200_run_ensemble.restype = C.c_int
+    lib.kmcb200_run_ensemble_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(EnsembleArgs)]
+    lib.kmcb200_run_ensemble_multi.restype = C.c_int
     lib.kmcb200_probe_rates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_void_p]
     lib.kmcb200_probe_rates.restype = C.c_int

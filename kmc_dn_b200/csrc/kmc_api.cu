@@ -4,6 +4,7 @@
 //         kernels (goSimulation/simulationWrapper.go:83-169, 274-316).
 // Part 2: lean ensemble API.
 // There is NO CPU fallback: without a CUDA device every entry point fails loudly.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -12,6 +13,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/kmc_b200.h"
@@ -369,6 +371,48 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     return 0;
 }
 
+// One process, several GPUs: members are independent Markov chains, so the ensemble is cut into
+// contiguous blocks, one per layout / device, each run by its own host thread through kmcb200_run_ensemble on its
+// slice of the caller's buffers.  Streams are numbered by global member index: same results as on one device.
+extern "C" int kmcb200_run_ensemble_multi(kmcb200_layout *const *layouts, int n_layouts, const kmcb200_ensemble_args *a) {
+    if (!layouts || n_layouts < 1 || !a) return fail("kmcb200_run_ensemble_multi: null argument");
+    for (int r = 0; r < n_layouts; ++r) {
+        if (!layouts[r]) return fail("kmcb200_run_ensemble_multi: null layout");
+        if (layouts[r]->dev.N != layouts[0]->dev.N || layouts[r]->dev.P != layouts[0]->dev.P)
+            return fail("kmcb200_run_ensemble_multi: the layouts must be copies of ONE layout on different devices");
+    }
+    if (a->flags & KMCB200_FLAG_DEVICE_PTRS) return fail("kmcb200_run_ensemble_multi: host pointers only");
+    if (a->stream) return fail("kmcb200_run_ensemble_multi: streams are per device; pass stream = NULL");
+    if (n_layouts == 1 || a->B < 2) return kmcb200_run_ensemble(layouts[0], a);
+    const int N = layouts[0]->dev.N, P = layouts[0]->dev.P, S = N + P;
+    const int64_t B = a->B, H = a->prehops + a->hops;
+    const int n = (int)(B < n_layouts ? B : n_layouts);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<int> rcs((size_t)n, 0);
+    std::vector<std::thread> th;
+    for (int r = 0; r < n; ++r) {
+        const int64_t base = B / n, rem = B % n;
+        const int64_t lo = r * base + (r < rem ? r : rem), cnt = base + (r < rem ? 1 : 0);
+        kmcb200_ensemble_args ar = *a;
+        ar.B = cnt;
+        ar.member_index0 = a->member_index0 + (uint64_t)lo;
+#define OFF(field, stride) if (a->field) ar.field = a->field + (size_t)lo * (size_t)(stride);
+        OFF(E_constant, N) OFF(electrode_v, P) OFF(kT, 1) OFF(occupation0, N)
+        OFF(stream_e, H) OFF(stream_u, H) OFF(stream_u64, 2 * H)
+        OFF(time, 1) OFF(electrode_occ, P) OFF(occupation_out, N) OFF(site_energies_out, S) OFF(avg_occupation, N)
+        OFF(traffic, (size_t)S * S) OFF(trace, 2 * a->hops) OFF(misses, 1) OFF(prob_occupation, N) OFF(prob_electrode_occ, P)
+#undef OFF
+        th.emplace_back([&, r, ar]() {
+            rcs[(size_t)r] = kmcb200_run_ensemble(layouts[r], &ar);
+            if (rcs[(size_t)r]) errs[(size_t)r] = g_err;  // (thread-local message of the worker)
+        });
+    }
+    for (auto &t : th) t.join();
+    for (int r = 0; r < n; ++r)
+        if (rcs[(size_t)r]) return fail("device " + std::to_string(layouts[r]->device) + ": " + errs[(size_t)r]);
+    return 0;
+}
+
 extern "C" int kmcb200_probe_rates(kmcb200_layout *lay, const double *E_constant, const double *electrode_v,
                                    double kT, const uint8_t *occupation, float *site_energies_io,
                                    int energies_given, float *rates_out) {
@@ -399,7 +443,7 @@ namespace {
 // Layout cache: the reference's callers pass the same tables over and over (dn_search.py:107-118,
 // voltage_search.py:138-157); keep the device copies keyed by content.
 struct LayoutKey {
-    int N, P; double nu, I_0, R, cut; uint64_t h1, h2;
+    int N, P; double nu, I_0, R, cut; uint64_t h1, h2; int device, pad_;
     bool operator<(const LayoutKey &o) const { return memcmp(this, &o, sizeof(LayoutKey)) < 0; }
 };
 std::mutex g_cache_mu;
@@ -411,11 +455,12 @@ uint64_t fnv(const double *p, size_t n, uint64_t h) {
     return h;
 }
 
-kmcb200_layout *cached_layout(int N, int P, const double *d, const double *tc, double nu, double I_0, double R, double cut) {
+kmcb200_layout *cached_layout(int N, int P, const double *d, const double *tc, double nu, double I_0, double R, double cut,
+                              int device = 0) {
     const size_t SS = (size_t)(N + P) * (N + P);
     LayoutKey k;
     memset(&k, 0, sizeof(k));
-    k.N = N; k.P = P; k.nu = nu; k.I_0 = I_0; k.R = R; k.cut = cut;
+    k.N = N; k.P = P; k.nu = nu; k.I_0 = I_0; k.R = R; k.cut = cut; k.device = device;
     k.h1 = fnv(d, SS, 0xcbf29ce484222325ULL); k.h2 = fnv(tc, SS, 0x84222325cbf29ce4ULL);
     std::lock_guard<std::mutex> lock(g_cache_mu);
     auto it = g_cache.find(k);
@@ -424,7 +469,7 @@ kmcb200_layout *cached_layout(int N, int P, const double *d, const double *tc, d
         for (auto &kv : g_cache) kmcb200_layout_destroy(kv.second);
         g_cache.clear();
     }
-    kmcb200_layout *lay = kmcb200_layout_create(0, N, P, d, tc, nu, I_0, R, cut);
+    kmcb200_layout *lay = kmcb200_layout_create(device, N, P, d, tc, nu, I_0, R, cut);
     if (lay) g_cache[k] = lay;
     return lay;
 }
@@ -578,7 +623,19 @@ extern "C" long long parallelSimulations(GoSlice NSites, GoSlice NElectrodes, Go
         a.E_constant = Ec.data(); a.electrode_v = V.data(); a.kT = kTs.data(); a.occupation0 = occ.data();
         a.seed = g_seed.load(); a.member_index0 = g_next_member.fetch_add(G);
         a.time = tm.data(); a.electrode_occ = eo.data();
-        if (kmcb200_run_ensemble(lay, &a)) die("parallelSimulations");
+        // large groups are spread over all the GPUs of the box (copies of the layout on the other devices)
+        const int ndev = kmcb200_device_count();
+        const int use = (int)std::min<size_t>((size_t)(ndev > 0 ? ndev : 1), std::max<size_t>(1, G / 2048));
+        if (use > 1) {
+            const Sim &s0 = sims[(size_t)idx[0]];
+            std::vector<kmcb200_layout *> lays((size_t)use, lay);
+            for (int dv = 1; dv < use; ++dv) {
+                lays[(size_t)dv] = cached_layout(N, P, distances.data + s0.offC, transitions_constant.data + s0.offC,
+                                                 nu.data[idx[0]], I_0.data[idx[0]], R.data[idx[0]], 0.0, dv);
+                if (!lays[(size_t)dv]) die("parallelSimulations");
+            }
+            if (kmcb200_run_ensemble_multi(lays.data(), use, &a)) die("parallelSimulations");
+        } else if (kmcb200_run_ensemble(lay, &a)) die("parallelSimulations");
         for (size_t q = 0; q < G; ++q) {
             const Sim &s = sims[(size_t)idx[q]];
             time.data[idx[q]] = tm[q];

@@ -105,13 +105,16 @@ class Layout:
         a.site_energies_out = _ptr(out.get("site_energies"))
         a.avg_occupation, a.traffic, a.trace = _ptr(out.get("avg_occupation")), _ptr(out.get("traffic")), _ptr(out.get("trace"))
         a.stream = cuda_stream
-        if self.lib.kmcb200_run_ensemble(self._h, C.byref(a)):
-            raise RuntimeError("kmcb200_run_ensemble: " + _lib.last_error())
+        self._call(a)
         if "occupation" in out:
             out["occupation"] = out["occupation"].astype(bool)
         with np.errstate(divide="ignore", invalid="ignore"):
             out["current"] = out["electrode_occupation"] / out["time"][:, None]  # kmc_dopant_networks.py:618
         return out
+
+    def _call(self, a):
+        if self.lib.kmcb200_run_ensemble(self._h, C.byref(a)):
+            raise RuntimeError("kmcb200_run_ensemble: " + _lib.last_error())
 
     # ------------------------------------------------------------------ device-pointer call (async)
     def run_device(self, B, hops, kT, electrode_v, time, electrode_occ, E_constant=None, basis=None, prehops=0,
@@ -172,3 +175,33 @@ class Layout:
 
 def launch_count():
     return int(_lib.load().kmcb200_launch_count())
+
+
+class MultiLayout(Layout):
+    """One layout replicated on several GPUs of the box, driven from ONE process: `run(...)` has Layout.run's
+    signature and results (streams are numbered by global member index), the members are cut into contiguous
+    blocks, one per device (kmcb200_run_ensemble_multi).  devices=None: all visible devices."""
+
+    def __init__(self, N, P, distances, transitions_constant, nu=1.0, I_0=100.0, R=1.0, prune_threshold=0.0, devices=None):
+        lib = _lib.load()
+        if devices is None:
+            devices = list(range(lib.kmcb200_device_count()))
+        if not devices:
+            raise RuntimeError("kmcb200: no CUDA device available (this library has no CPU fallback)")
+        super().__init__(N, P, distances, transitions_constant, nu, I_0, R, prune_threshold, device=devices[0])
+        self.devices = list(devices)
+        self._others = [Layout(N, P, distances, transitions_constant, nu, I_0, R, prune_threshold, device=d) for d in devices[1:]]
+
+    def _call(self, a):
+        hs = [self._h] + [o._h for o in self._others]
+        arr = (C.c_void_p * len(hs))(*hs)
+        if self.lib.kmcb200_run_ensemble_multi(arr, len(hs), C.byref(a)):
+            raise RuntimeError("kmcb200_run_ensemble_multi: " + _lib.last_error())
+
+    def run_device(self, *args, **kw):
+        raise RuntimeError("MultiLayout works on host buffers; use one Layout per device for device pointers")
+
+    def close(self):
+        for o in getattr(self, "_others", []):
+            o.close()
+        super().close()

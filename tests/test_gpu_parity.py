@@ -394,6 +394,37 @@ def test_random_layouts_memoisation_and_trace_consistency():
             np.testing.assert_array_equal(a["electrode_occupation"][m], eo, err_msg=str(tag))
 
 
+def test_multi_device_entry_equals_single_device(fixtures_subset):
+    """kmcb200_run_ensemble_multi (one process, one host thread per layout copy) returns exactly what one device
+    returns: the members are cut into contiguous blocks and streams are numbered by global member index.  With one
+    GPU the copies live on the same device (the sharding, offsets and threading are what is under test); with
+    several they are spread over all of them."""
+    from kmc_dn_b200 import _lib
+    from kmc_dn_b200.ensemble import Layout, MultiLayout
+    c = _fixture_case(fixtures_subset["XOR_wide/test0"])
+    ndev = _lib.load().kmcb200_device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0, 0]
+    rng = np.random.default_rng(4)
+    B = 1003  # ragged
+    V = np.tile(c["electrode_v"], (B, 1)) + rng.normal(0, 20, (B, c["P"]))
+    E = np.tile(c["E_constant"], (B, 1)) + rng.normal(0, 1, (B, c["N"]))
+    kT = rng.uniform(0.5, 2.0, B)
+    one = Layout(c["N"], c["P"], c["distances"], c["transitions_constant"], nu=c["nu"], I_0=c["I_0"], R=c["R"])
+    many = MultiLayout(c["N"], c["P"], c["distances"], c["transitions_constant"], nu=c["nu"], I_0=c["I_0"], R=c["R"],
+                       devices=devices)
+    kw = dict(E_constant=E, occupation0=c["occupation"], prehops=100, seed=5, member_index0=77, want_occupation=True,
+              want_site_energies=True, record=True, trace=True)
+    a = one.run(700, kT, V, **kw)
+    b = many.run(700, kT, V, **kw)
+    for k in ("time", "electrode_occupation", "occupation", "site_energies", "avg_occupation", "traffic", "trace"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    a = one.run(3000, kT, V, E_constant=E, seed=6)
+    b = many.run(3000, kT, V, E_constant=E, seed=6)
+    np.testing.assert_array_equal(a["time"], b["time"])
+    np.testing.assert_array_equal(a["electrode_occupation"], b["electrode_occupation"])
+    one.close(); many.close()
+
+
 def test_superposition_matvec_equals_explicit_E_constant(fixtures_subset):
     """E_constant[m,:] = basis[P,:] + V[m,:] @ basis[:P,:] on device == passing E_constant explicitly."""
     f = fixtures_subset["XOR_wide/test0"]
