@@ -42,6 +42,41 @@ def evaluate_fixture(d, hops, runs=5, seed=0):
     return D, cur
 
 
+def compact_fixtures(npz_path):
+    """Iterates over tests/golden/fixtures_all.npz (all 400 fixtures of the reference in compact form, written by
+    oracle/make_golden.py): yields (name, dict) with the fields evaluate_fixture needs; distances and
+    transitions_constant are rebuilt from the positions as kmc_dopant_networks.py:657-695, 824-830 does."""
+    z = np.load(npz_path)
+    for i, name in enumerate(z["names"]):
+        nu, kT, I_0, R, ab = (float(x) for x in z["scalars"][i])
+        pos = np.vstack([z["acceptors"][i], z["electrodes"][i][:, :3]])
+        dist = np.sqrt(((pos[:, None] - pos[None]) ** 2).sum(-1))
+        tc = nu * np.exp(-2 * dist / ab) - np.eye(len(pos))
+        yield str(name), dict(N=z["acceptors"].shape[1], P=z["electrodes"].shape[1], nu=nu, kT=kT, I_0=I_0, R=R,
+                              distances=dist, transitions_constant=tc, electrodes=z["electrodes"][i],
+                              E_constant=z["E_constant"][i], mean_currents=z["mean_currents"][i],
+                              stddev_currents=z["stddev_currents"][i])
+
+
+def acceptance_over_sets(npz_path, stride_5m=1, seed0=0, stride_1m=1):
+    """The reference's acceptance run (validate_tests.py:299-350) over its four fixture sets at the fixtures' own run
+    lengths (1e6 hops, 5e6 for the *5M sets).  Returns {set: dict(fixtures, pairs, D_mean, D_median, extreme)}."""
+    per = {}
+    for k, (name, d) in enumerate(compact_fixtures(npz_path)):
+        setname, t = name.split("/")
+        big = setname.endswith("5M")
+        if int(t[4:]) % (stride_5m if big else stride_1m):
+            continue
+        D, _ = evaluate_fixture(d, 5_000_000 if big else 1_000_000, seed=seed0 + k)
+        per.setdefault(setname, []).append(D)
+    out = {}
+    for setname, Ds in per.items():
+        Ds = np.array(Ds)
+        out[setname] = dict(fixtures=int(len(Ds)), pairs=int(Ds.size), D_mean=float(Ds.mean()), D_median=float(np.median(Ds)),
+                            extreme=float((Ds > 0.9).mean()))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("directory")

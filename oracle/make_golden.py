@@ -14,6 +14,10 @@ Run:  python oracle/make_golden.py
    mean/stddev currents that validate_tests.py:80-135 accepts against.
 3. electrostatics.npz -- electrodes, acceptor/donor positions and the stored
    eV_constant / comp_constant of fixtures (pins the FD-Laplace front end).
+5. fixtures_all.npz -- ALL 400 fixtures in compact form (positions, electrode voltages, E_constant, scalars and
+   the stored 5-run mean / stddev currents; distances and transitions_constant follow from the positions exactly
+   as kmc_dopant_networks.py:657-695, 824-830 builds them, which is asserted here) for the full-size run of the
+   reference's acceptance test (thesis_indrek/validate_tests.py:80-135, 299-350).
 """
 import glob
 import os
@@ -105,8 +109,30 @@ def layouts():
     np.savez_compressed(os.path.join(OUT, "layouts.npz"), acceptor_layouts=a[:4], donor_layouts=d[:4])
 
 
+def fixtures_all():
+    sets = ["rnd_min_max", "rnd_min_max5M", "XOR_wide", "XOR_wide5M"]
+    cols = {k: [] for k in ("acceptors", "donors", "electrodes", "E_constant", "occupation", "mean_currents",
+                            "stddev_currents", "scalars")}
+    names = []
+    for setname in sets:
+        for i in range(100):
+            d = load_kmc(f"{REF}/thesis_indrek/tests/{setname}/test{i}.kmc")
+            pos = np.vstack([d["acceptors"], d["electrodes"][:, :3]])
+            dist = np.sqrt(((pos[:, None] - pos[None]) ** 2).sum(-1))
+            tc = d["nu"] * np.exp(-2 * dist / d["ab"]) - np.eye(len(pos))
+            assert np.abs(dist - d["distances"]).max() <= 1e-15 and np.abs(tc - d["transitions_constant"]).max() <= 1e-15
+            names.append(f"{setname}/test{i}")
+            for k in ("acceptors", "donors", "electrodes", "E_constant", "mean_currents", "stddev_currents"):
+                cols[k].append(np.asarray(d[k], dtype=np.float64))
+            cols["occupation"].append(np.asarray(d["occupation"], dtype=np.uint8))
+            cols["scalars"].append(np.array([d["nu"], d["kT"], d["I_0"], d["R"], d["ab"]], dtype=np.float64))
+    np.savez_compressed(os.path.join(OUT, "fixtures_all.npz"), names=np.array(names),
+                        **{k: np.stack(v) for k, v in cols.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    fixtures_all()
     ref, seed_fn = numba_ref.load()
     cases = {
         "c1_basic_N10_P2": (synthetic_case(10, 2, 0), 11, 4000, 1500),

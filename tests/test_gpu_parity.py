@@ -258,6 +258,26 @@ def test_fast_kernel_currents_pass_reference_acceptance(fixtures_subset):
     assert np.median(rel) < 0.02 and rel.max() < 0.15, (np.median(rel), rel.max())
 
 
+def test_reference_acceptance_over_the_fixture_sets():
+    """The reference's acceptance run (thesis_indrek/validate_tests.py:299-350) at the fixtures' own run lengths:
+    every 2nd fixture of rnd_min_max and XOR_wide (1e6 hops x 5 runs each) and every 10th of the 5e6-hop sets,
+    per-electrode Bhattacharyya distance against the stored 5-run statistics (which the reference produced with
+    wrapperSimulateRecordPlus, generate_tests.py:45-63).  The run over ALL 400 fixtures is profiles/run_acceptance.py
+    -> profiles/acceptance_r01.json: D_mean 0.198 / 0.143 / 0.373 / 0.217, extreme 1.9 / 0.9 / 6.6 / 2.0 % on
+    rnd_min_max / rnd_min_max5M / XOR_wide / XOR_wide5M.  Calibration: the CPU oracle (restated Go loop, its own RNG)
+    scores D_mean 0.204 / extreme 1.8 % on rnd_min_max and D_mean 0.384 / extreme 6.4 % on XOR_wide against the same
+    fixtures; two 5-run samples of one distribution cannot do much better."""
+    import os
+    from kmc_dn_b200.validate import acceptance_over_sets
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures_all.npz")
+    res = acceptance_over_sets(path, stride_5m=10, stride_1m=2)
+    assert res["rnd_min_max"]["fixtures"] == 50 and res["XOR_wide"]["fixtures"] == 50 and res["XOR_wide5M"]["fixtures"] == 10
+    for setname, r in res.items():
+        assert r["D_mean"] < 0.7, (setname, r)
+        assert r["extreme"] < 0.2, (setname, r)
+    assert res["rnd_min_max"]["D_median"] < 0.2 and res["XOR_wide"]["D_median"] < 0.25, res
+
+
 def test_fast_kernel_ensemble_mean_within_confidence_interval_of_oracle(golden_py):
     """Ensemble-averaged currents: 256 GPU members vs 256 oracle members (simulateRecordPlus semantics, own
     RNG).  |mean_gpu - mean_cpu| <= 4.5 * sqrt(se_gpu^2 + se_cpu^2) per electrode (two-sample z, ~1e-5 false
