@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
     sts_f(a_mir + 128 + lane * 4, ve_mine);
     __syncwarp();
     if (K > 0) {  // empty caches: a key that hashes to another slot can never hit
-        if (lane < K) sts_u(a_cache + lane * ENTB + 260, lane == 0 ? 1u : 0u);
+        for (int e_ = lane; e_ < K; e_ += 32) sts_u(a_cache + e_ * ENTB + 260, e_ == 0 ? 1u : 0u);
     }
     const uint2 tag = make_uint2(E.launch_id, (uint32_t)m + 1u);
 
@@ -785,6 +785,7 @@ template <int PT>
 static cudaError_t launch_memo_p(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
     switch (logk) {
         case -1: return launch_memo_t<PT, -1>(L, E, st, launches, plan);
+        case 6: return launch_memo_t<PT, 6>(L, E, st, launches, plan);
         default: return launch_memo_t<PT, 4>(L, E, st, launches, plan);
     }
 }

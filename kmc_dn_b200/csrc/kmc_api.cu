@@ -309,7 +309,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         // second-level entries per warp slot: enough that a trajectory's few hundred states rarely collide in the
         // direct-mapped table (conflict misses: 1.5 % of the hops at 256 entries, 0.1 % at 1024 on a 1e6-hop C3 member)
         const int64_t th = a->hops + a->prehops;
-        int logk = 4, glog = th < 30000 ? 9 : (th < 300000 ? 10 : 12);
+        // first-level entries per warp: 16 when the SMs are full of trajectories (shared memory is what limits the resident
+        // warps), 64 for small ensembles -- a lone trajectory sees the full latency of every first-level miss
+        int logk = (narrow && B <= 1024) ? 6 : 4, glog = th < 30000 ? 9 : (th < 300000 ? 10 : 12);
         if (const char *ev = getenv("KMCB200_MEMO_LOGK")) logk = atoi(ev);
         if (const char *ev = getenv("KMCB200_GTAB_LOG")) glog = atoi(ev);
         if (a->flags & KMCB200_FLAG_NO_MEMO) logk = -1;
