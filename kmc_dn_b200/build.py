@@ -47,16 +47,29 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.abspath(__file__)]
-    objs = []
+    objs, jobs = [], []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + deps):
-            cmd = [nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            jobs.append([nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+    if jobs:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
-                print(" ".join(cmd))
-            subprocess.check_call(cmd)
+                print(" ".join(cmd), flush=True)
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            return cmd, r
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(run, jobs))
+        for cmd, r in results:
+            if verbose or r.returncode:
+                sys.stdout.write(r.stdout)
+                sys.stderr.write(r.stderr)
+            if r.returncode:
+                raise subprocess.CalledProcessError(r.returncode, cmd)
     if force or _stale(SO, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", SO] + objs + ["-Xlinker", "--exclude-libs=ALL"]
         if verbose:
