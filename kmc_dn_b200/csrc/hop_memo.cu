@@ -1,4 +1,4 @@
-// hop_memo.cu -- production KMC hop loop with STATE MEMOISATION (KMCB200_MODE_FAST, N <= 32 acceptors).
+// hop_memo.cu -- production KMC hop loop with STATE MEMOISATION (KMCB200_MODE_FAST, N <= 31 acceptors).
 //
 // Reference semantics being accelerated (MUTUEL/kmc_dn, paths relative to the reference tree):
 //   site energies      goSimulation/simulation.go:226-234  (E_const - I0*R*sum_{j empty} 1/d_ij)
@@ -22,15 +22,20 @@
 // cumulative rate structure is a PURE function of the occupation bit-mask, because the fp64 incremental
 // energies are exact.  Every warp keeps a direct-mapped cache in shared memory:
 //
-//     key   = 32-bit occupation mask              (slot = multiplicative hash, 2^LOGK slots)
-//     value = per lane its LARGEST rate as a NORMALISED fp64 exclusive prefix over the lanes (with the event -- the
-//             partner site and the direction -- in the 7 mantissa LSBs), lane 31 = the normalised mass of these top
-//             events (sentinel), the fp32 reciprocal of the total rate and the fp64 total (272 B)
+//     key   = 32-bit occupation mask              (slot = multiplicative hash, 2^LOGK slots: 16, or 64 for small ensembles)
+//     value = 31 event SLOTS as a NORMALISED fp64 exclusive prefix (with the event -- partner site and direction, for
+//             NR > 1 also the acceptor -- in the 7 / 12 mantissa LSBs), lane 31 = the normalised mass of the slot events
+//             (sentinel), the fp32 reciprocal of the total rate and the fp64 total (272 B).
+//             Slot s holds the (s / N + 1)-th largest rate of acceptor s % N: for N >= 25 simply every acceptor's
+//             largest event (NR = 1); smaller layouts leave lanes free for the 2nd / 3rd largest (NR = 2 / 3) -- on a
+//             regular grid all downhill hops of an acceptor have the SAME rate, and one event per acceptor would
+//             leave 10 % of the mass to the slow path.
+//     A second level of the same entries (+ a (launch, member) tag, so it is never reset) lives in global memory / L2.
 //
 // Hit:  the sweep and the fp64 scan are skipped; the hop costs ONE ballot of (key matches && prefix < uniform) on the
 //       speculatively prefetched line -- an empty ballot means another state's line, the sentinel lane (the 0.2 % of
 //       the hops that fall outside the top events take the exact slow path) or a dead state --, one shuffle for the
-//       winning lane's event code and a branch-free update of the mask and the electrode tallies: 29 SASS
+//       winning lane's event code and a branch-free update of the mask and the electrode tallies: 27 SASS
 //       instructions per hop.
 // Miss: sweep + scan, then the prefix is parked in the slot.
 // Memoising a pure function cannot change a result: with the cache disabled (LOGK = -1 instantiation,
