@@ -14,6 +14,8 @@ SO_PATH = os.path.join(HERE, "libkmcb200.so")
 MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER, MODE_PROB = 0, 1, 2, 3, 4, 5
 FLAG_DEVICE_PTRS = 1
 FLAG_NO_MEMO = 2
+FLAG_LANES = 4      # force the thread-per-trajectory kernel (hop_lanes.cu)
+FLAG_NO_LANES = 8   # never use it
 
 
 class GoSlice(C.Structure):

@@ -19,6 +19,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 UNITS = {
     "hop_fast.cu": [],
     "hop_memo.cu": [],
+    "hop_lanes.cu": [],
     "hop_wide.cu": [],
     "hop_reforder.cu": [],
     "hop_exact.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
@@ -26,7 +27,7 @@ UNITS = {
     "kmc_api.cu": [],
     "peaks.cu": [],
 }
-DEPS = ["kmc_internal.cuh", "kmc_device.cuh", os.path.join("..", "..", "include", "kmc_b200.h")]
+DEPS = ["kmc_internal.cuh", "kmc_device.cuh", "memo_common.cuh", os.path.join("..", "..", "include", "kmc_b200.h")]
 
 
 def _nvcc():

@@ -50,6 +50,10 @@ struct kmcb200_layout {
     void *gtab = nullptr;
     size_t gtab_bytes = 0;
     uint32_t launch_id = 0;  // tag of the second-level entries (kmc_internal.cuh)
+    // state table of the thread-per-trajectory kernel (hop_lanes.cu: warp_slots x 2^tlog x 256 B), grow-only
+    void *ltab = nullptr;
+    size_t ltab_bytes = 0;
+    uint32_t lanes_launch_id = 0;
     unsigned long long *queue = nullptr;  // member work queue of the persistent kernel
     std::mutex mu;
 };
@@ -169,6 +173,7 @@ extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
     cudaFree(lay->ws);
     cudaFree(lay->gtab);
+    cudaFree(lay->ltab);
     cudaFree(lay->queue);
     delete lay;
 }
@@ -185,6 +190,9 @@ struct Carver {  // bump allocator over the layout workspace, 256-byte aligned
 };
 size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 }  // namespace
+
+// MODE_FAST, N <= 31: ensembles of at least this many members run on the thread-per-trajectory kernel (hop_lanes.cu)
+static const int64_t kLanesAutoMinB = INT64_MAX;
 
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");
@@ -304,11 +312,68 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     else if (exact) le = launch_exact(D, E, st, &launches);
     else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
     else if (!getenv("KMCB200_NO_MEMO_KERNEL")) {
-        // memoised production kernels: hop_memo.cu (N <= 31: one mask word, sentinel lane) / hop_wide.cu (N <= 256)
+        // memoised production kernels: hop_lanes.cu (N <= 31, large ensembles: one thread per trajectory on the hit path),
+        // hop_memo.cu (N <= 31: one warp per trajectory, one mask word, sentinel lane) / hop_wide.cu (N <= 256)
         const bool narrow = D.N <= 31;
+        const int64_t th = a->hops + a->prehops;
+        if (!lay->queue) CU(cudaMalloc((void **)&lay->queue, 256));
+        CU(cudaMemsetAsync(lay->queue, 0, 256, st));
+        E.queue = lay->queue;
+        // ---- thread-per-trajectory kernel: when the ensemble fills the device with 32 trajectories per warp
+        //      (below that the warp-per-trajectory kernel has more parallelism to offer)
+        bool lanes = false;
+        {
+            const bool lanes_ok = narrow && !E.stream_e && !E.avg_occupation && !E.traffic;
+            if (a->flags & KMCB200_FLAG_LANES) {
+                if (!lanes_ok) return fail("kmcb200_run_ensemble: the thread-per-trajectory kernel needs N <= 31 and has no record / injected-stream outputs");
+                lanes = true;
+            } else if (!(a->flags & KMCB200_FLAG_NO_LANES) && lanes_ok) {
+                lanes = B >= kLanesAutoMinB && !(a->flags & KMCB200_FLAG_NO_MEMO);
+                if (const char *ev = getenv("KMCB200_LANES")) lanes = atoi(ev) != 0;
+            }
+        }
+        if (lanes) {
+            E.lanes_flags = (a->flags & KMCB200_FLAG_NO_MEMO) ? 1 : 0;
+            E.gtab = nullptr; E.gtab_log = 6;
+            if (!(E.lanes_flags & 1)) {
+                // table entries per warp slot (shared by the warp's runs of identical members: a run of g gets g/32 of them)
+                int tlog = th < 30000 ? 12 : 13;
+                if (const char *ev = getenv("KMCB200_LTAB_LOG")) tlog = atoi(ev);
+                if (tlog < 6) tlog = 6;
+                if (tlog > 16) tlog = 16;
+                MemoPlan plan{0};
+                le = launch_lanes(D, E, st, nullptr, &plan);
+                if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
+                size_t bytes = ((size_t)plan.warp_slots << tlog) * 256;
+                if (bytes > lay->ltab_bytes) {
+                    if (lay->ltab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ltab)); lay->ltab = nullptr; lay->ltab_bytes = 0; }
+                    while (tlog >= 6 && cudaMalloc(&lay->ltab, bytes) != cudaSuccess) {  // a cache: halve it until it fits
+                        (void)cudaGetLastError();
+                        lay->ltab = nullptr;
+                        --tlog;
+                        bytes >>= 1;
+                    }
+                    if (tlog >= 6) {
+                        lay->ltab_bytes = bytes;
+                        CU(cudaMemsetAsync(lay->ltab, 0, bytes, st));  // once: launch id 0 never matches
+                        lay->lanes_launch_id = 0;
+                    }
+                }
+                if (tlog >= 6) {
+                    if (++lay->lanes_launch_id == 0) {
+                        CU(cudaMemsetAsync(lay->ltab, 0, lay->ltab_bytes, st));
+                        lay->lanes_launch_id = 1;
+                    }
+                    // (a table left over from a larger launch is simply used at the requested size)
+                    E.gtab = (unsigned char *)lay->ltab; E.gtab_log = tlog; E.launch_id = lay->lanes_launch_id;
+                } else if (a->flags & KMCB200_FLAG_LANES) return fail("kmcb200_run_ensemble: no device memory for the state table");
+                else lanes = false;
+            }
+        }
+        if (lanes) le = launch_lanes(D, E, st, &launches);
+        else {
         // second-level entries per warp slot: enough that a trajectory's few hundred states rarely collide in the
         // direct-mapped table (conflict misses: 1.5 % of the hops at 256 entries, 0.1 % at 1024 on a 1e6-hop C3 member)
-        const int64_t th = a->hops + a->prehops;
         // first-level entries per warp: 16 when the SMs are full of trajectories (shared memory is what limits the resident
         // warps), 64 for small ensembles -- a lone trajectory sees the full latency of every first-level miss
         int logk = (narrow && B <= 1024) ? 6 : 4, glog = th < 30000 ? 9 : (th < 300000 ? 10 : 12);
@@ -346,10 +411,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                 E.gtab = (unsigned char *)lay->gtab; E.gtab_log = glog; E.launch_id = lay->launch_id;
             }
         }
-        if (!lay->queue) CU(cudaMalloc((void **)&lay->queue, 256));
-        CU(cudaMemsetAsync(lay->queue, 0, 256, st));
-        E.queue = lay->queue;
         le = narrow ? launch_memo(D, E, logk, st, &launches) : launch_wide(D, E, logk, st, &launches);
+        }
     } else le = launch_fast(D, E, st, &launches);
     g_launches += launches;
     if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));

@@ -43,6 +43,7 @@ struct EnsembleDev {
     unsigned long long *queue;  // memoised kernel: member work queue (zeroed before the launch)
     unsigned char *gtab;  // memoised kernels: second-level cache, warp_slots * 2^gtab_log entries of 288 / 448 B (or null)
     int gtab_log;         // log2(entries per warp slot); 0 = no second level
+    int lanes_flags;      // hop_lanes.cu: bit 0 = do not consult the table (every hop is evaluated; for testing)
     uint32_t launch_id;   // entries are valid only with the tag (launch_id, member + 1): the table is zeroed ONCE, at
                           // allocation, and never reset -- neither per launch nor per member
 };
@@ -54,6 +55,8 @@ cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cuda
                         MemoPlan *plan_only = nullptr);
 cudaError_t launch_wide(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
                         MemoPlan *plan_only = nullptr);
+cudaError_t launch_lanes(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches,
+                         MemoPlan *plan_only = nullptr);
 cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_prob(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_exact(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);

@@ -11,7 +11,15 @@ import numpy as np
 
 from . import _lib
 from ._lib import (MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER, MODE_PROB,  # noqa: F401
-                   FLAG_DEVICE_PTRS, FLAG_NO_MEMO)
+                   FLAG_DEVICE_PTRS, FLAG_NO_MEMO, FLAG_LANES, FLAG_NO_LANES)
+
+
+def _kernel_flags(kernel):
+    """kernel: None = the library chooses; 'lanes' = thread-per-trajectory kernel (hop_lanes.cu); 'warp' = warp-per-
+    trajectory kernels (hop_memo.cu / hop_wide.cu)."""
+    if kernel in (None, 'auto'):
+        return 0
+    return {'lanes': FLAG_LANES, 'warp': FLAG_NO_LANES}[kernel]
 
 
 def _host(a, dtype):
@@ -61,7 +69,8 @@ class Layout:
     # ------------------------------------------------------------------ host-buffer call
     def run(self, hops, kT, electrode_v, E_constant=None, basis=None, prehops=0, mode=MODE_FAST, occupation0=None,
             seed=0, member_index0=0, stream_e=None, stream_u=None, stream_u64=None, want_occupation=False,
-            want_site_energies=False, record=False, trace=False, want_misses=False, memo=True, cuda_stream=None):
+            want_site_energies=False, record=False, trace=False, want_misses=False, memo=True, cuda_stream=None,
+            kernel=None):
         """Run B members; every array is a host numpy array.  Returns a dict."""
         N, P, S = self.N, self.P, self.S
         V = _host(np.atleast_2d(electrode_v), np.float64)
@@ -95,6 +104,7 @@ class Layout:
             out["misses"] = np.zeros(B, dtype=np.int64)
         a = _lib.EnsembleArgs()
         a.B, a.hops, a.prehops, a.mode, a.flags = B, int(hops), int(prehops), int(mode), (0 if memo else FLAG_NO_MEMO)
+        a.flags |= _kernel_flags(kernel)
         a.E_constant, a.basis, a.electrode_v, a.kT = _ptr(Ec), _ptr(bs), _ptr(V), _ptr(kTa)
         a.occupation0 = _ptr(occ0)
         a.misses = _ptr(out.get("misses"))
@@ -119,12 +129,12 @@ class Layout:
     # ------------------------------------------------------------------ device-pointer call (async)
     def run_device(self, B, hops, kT, electrode_v, time, electrode_occ, E_constant=None, basis=None, prehops=0,
                    mode=MODE_FAST, occupation0=None, seed=0, member_index0=0, occupation_out=None,
-                   memo=True, cuda_stream=None):
+                   memo=True, cuda_stream=None, kernel=None):
         """Every array argument is a device tensor (torch) or raw device pointer holder with
         .data_ptr(); enqueues on `cuda_stream` and returns immediately."""
         a = _lib.EnsembleArgs()
         a.B, a.hops, a.prehops, a.mode = int(B), int(hops), int(prehops), int(mode)
-        a.flags = FLAG_DEVICE_PTRS | (0 if memo else FLAG_NO_MEMO)
+        a.flags = FLAG_DEVICE_PTRS | (0 if memo else FLAG_NO_MEMO) | _kernel_flags(kernel)
         a.E_constant, a.basis, a.electrode_v, a.kT = _ptr(E_constant), _ptr(basis), _ptr(electrode_v), _ptr(kT)
         a.occupation0 = _ptr(occupation0)
         a.seed, a.member_index0 = int(seed) & (2**64 - 1), int(member_index0)
