@@ -44,6 +44,8 @@
 //
 // RNG: the same Philox4x32-10 numbering as hop_memo.cu (key = seed, counter = (64-hop block * 32 + pair, global member
 // index), two hops per call), so streams do not depend on batching, on the number of GPUs or on the kernel's geometry.
+#include <cstdlib>
+
 #include "memo_common.cuh"
 
 namespace kmcb200 {
@@ -57,17 +59,38 @@ template <int PT>
 struct LanesGeom {
     static constexpr int PV = PT > 0 ? PT : 32;   // electrode slots per trajectory
     static constexpr int MIRB = 256;              // mirror: acceptor energies (128 B) | electrode energies (128 B)
-    static constexpr int SRTB = 256;              // sort scratch: 32 x {rate, code}
     static constexpr int EFB = 32 * 32 * 4;       // E_constant (the narrowed fp32 values) of the 32 trajectories
     static constexpr int VEB = 32 * PV * 4;       // electrode energies of the 32 trajectories
     static constexpr int TALB = PV * 32 * 4;      // electrode tallies [electrode][trajectory]
-    static constexpr int WARP_BYTES = MIRB + SRTB + EFB + VEB + TALB;
+    static constexpr int WARP_BYTES = MIRB + EFB + VEB + TALB;
 };
 
 __device__ __forceinline__ uint4 ldg_u4(const unsigned char *p) {
     uint4 v;
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
+}
+// header + first chunk (thresholds, codes; 64 B) in ONE statement: the loads are issued back to back, one latency
+__device__ __forceinline__ void ldg_head(const unsigned char *p, uint4 &h, uint4 &a, uint4 &b, uint4 &c) {
+    asm volatile(
+        "ld.global.v4.u32 {%0, %1, %2, %3}, [%16];\n\t"
+        "ld.global.v4.u32 {%4, %5, %6, %7}, [%16+16];\n\t"
+        "ld.global.v4.u32 {%8, %9, %10, %11}, [%16+32];\n\t"
+        "ld.global.v4.u32 {%12, %13, %14, %15}, [%16+48];"
+        : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w),
+          "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+        : "l"(p)
+        : "memory");
+}
+// thresholds + codes of a later chunk (48 B at p)
+__device__ __forceinline__ void ldg_chunk(const unsigned char *p, uint4 &a, uint4 &b, uint4 &c) {
+    asm volatile(
+        "ld.global.v4.u32 {%0, %1, %2, %3}, [%12];\n\t"
+        "ld.global.v4.u32 {%4, %5, %6, %7}, [%12+16];\n\t"
+        "ld.global.v4.u32 {%8, %9, %10, %11}, [%12+32];"
+        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+        : "l"(p)
+        : "memory");
 }
 __device__ __forceinline__ uint32_t ldg_u16(const unsigned char *p) {
     uint32_t v;
@@ -82,8 +105,10 @@ __device__ __forceinline__ void stg_u16(unsigned char *p, uint32_t v) {
     asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.global.u16 [%0], t; }" ::"l"(p), "r"(v) : "memory");
 }
 
-template <int PT, bool DBG, int NR>
-__global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const LayoutDev L, const EnsembleDev E) {
+// MINB: resident CTAs per SM the register budget is set for; PF: fetch the entry of the NEXT state right after a hop is
+// applied (the loads fly while the next hop's variates are generated)
+template <int PT, bool DBG, int NR, int MINB, bool PF>
+__global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = LanesGeom<PT>;
     constexpr int PV = G::PV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,7 +134,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
-    const uint32_t a_mir = wb, a_srt = wb + G::MIRB, a_ef = a_srt + G::SRTB, a_ve = a_ef + G::EFB, a_tal = a_ve + G::VEB;
+    const uint32_t a_mir = wb, a_ef = wb + G::MIRB, a_ve = a_ef + G::EFB, a_tal = a_ve + G::VEB;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
@@ -201,6 +226,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         float t_part = 0.0f;
         long long n_miss = 0;
         uint4 r = make_uint4(0u, 0u, 0u, 0u);
+        uint4 hd = make_uint4(0u, 0u, 0u, 0u), ta = hd, tb = hd, tc = hd;  // (launch ids start at 1: never a valid header)
+        if (PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, ta, tb, tc);
 
         for (int64_t h = 0; h < total_hops; ++h) {
             if (h == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
@@ -228,30 +255,26 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             uint32_t code = 0;
             float rt = 0.0f;
             bool hit = false, slow = false;
-            if (alive && use_table) {
-                const unsigned char *ent = tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB;
-                const uint4 hd = ldg_u4(ent);
-                uint4 ta = ldg_u4(ent + 16), tb = ldg_u4(ent + 32);
-                hit = hd.x == occ && hd.z == tagx && hd.w == tagy;
-                if (hit) {
-                    rt = __uint_as_float(hd.y);
-                    const unsigned char *cp = ent;
-                    int c = 0;
-                    for (;;) {
-                        if (xr < tb.w) {
-                            const int k = (int)(xr >= ta.x) + (int)(xr >= ta.y) + (int)(xr >= ta.z) + (int)(xr >= ta.w) +
-                                          (int)(xr >= tb.x) + (int)(xr >= tb.y) + (int)(xr >= tb.z);
-                            code = ldg_u16(cp + 48 + 2 * k);
-                            break;
-                        }
-                        if (++c == 4) {
-                            slow = true;
-                            break;
-                        }
-                        cp += 64;
-                        ta = ldg_u4(cp + 16);
-                        tb = ldg_u4(cp + 32);
+            if (!PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, ta, tb, tc);
+            // (thresholds never decrease: the last clause is always true for a valid entry -- it keeps ptxas from
+            //  sinking the threshold loads below the branch, which would cost a second round trip)
+            hit = alive && use_table && hd.x == occ && hd.z == tagx && hd.w == tagy && tb.w >= ta.x;
+            if (hit) {
+                rt = __uint_as_float(hd.y);
+                int c = 0;
+                for (;;) {
+                    if (xr < tb.w) {
+                        const int k = (int)(xr >= ta.x) + (int)(xr >= ta.y) + (int)(xr >= ta.z) + (int)(xr >= ta.w) +
+                                      (int)(xr >= tb.x) + (int)(xr >= tb.y) + (int)(xr >= tb.z);
+                        const uint32_t w2 = (k & 4) ? ((k & 2) ? tc.w : tc.z) : ((k & 2) ? tc.y : tc.x);
+                        code = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
+                        break;
                     }
+                    if (++c == 4) {
+                        slow = true;
+                        break;
+                    }
+                    ldg_chunk(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB + (uint32_t)c * 64u + 16u, ta, tb, tc);
                 }
             }
 
@@ -314,20 +337,21 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 if (build) {
                     const double inv = 1.0 / total;
                     const float rtot = (float)inv;
-                    // rank of this slot among the 32 by decreasing rate (ties: lower slot first)
-                    int rank = 0;
+                    // slots by decreasing rate: bitonic network on (rate bits with the 5 low mantissa bits replaced by
+                    // 31 - slot) -- unique keys; the order only decides which events share the first chunk, not the result
+                    uint32_t skey = (__float_as_uint(sv) & ~31u) | (uint32_t)(31 - lane);
 #pragma unroll
-                    for (int d = 1; d < 32; ++d) {
-                        const int ol = (lane + d) & 31;
-                        const float ov = __shfl_sync(FULL, sv, ol);
-                        rank += (int)(ov > sv || (ov == sv && ol < lane));
+                    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                            const uint32_t other = __shfl_xor_sync(FULL, skey, jj);
+                            const bool keepmax = ((lane & jj) == 0) == ((lane & kk) == 0);
+                            skey = keepmax ? max(skey, other) : min(skey, other);
+                        }
                     }
-                    __syncwarp();
-                    sts_f(a_srt + (uint32_t)rank * 8u, sv);
-                    sts_u(a_srt + (uint32_t)rank * 8u + 4u, mycode);
-                    __syncwarp();
-                    const float ssv = lds_f(a_srt + lane * 8u);
-                    const uint32_t scode = lds_u(a_srt + lane * 8u + 4u);
+                    const int ssrc = 31 - (int)(skey & 31u);
+                    const float ssv = __shfl_sync(FULL, sv, ssrc);
+                    const uint32_t scode = __shfl_sync(FULL, mycode, ssrc);
                     const double incl = scan_d((double)ssv);
                     const uint32_t thr = __double2uint_rn(incl * inv * 4294967296.0);  // (saturates at 2^32 - 1)
                     if (use_table) {
@@ -461,6 +485,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                     tp[0] = from;
                     tp[1] = to;
                 }
+                if (PF && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, ta, tb, tc);
             }
         }
 
@@ -489,16 +514,17 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     }  // blocks of members
 }
 
-template <int PT>
-static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
+template <int PT, int MINB, bool PF>
+static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     using G = LanesGeom<PT>;
     const bool dbg = E.trace || E.misses;
     const int warps = 4;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
-    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3> : kmc_lanes_kernel<PT, false, 3>)
-              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2> : kmc_lanes_kernel<PT, false, 2>)
-                        : (dbg ? kmc_lanes_kernel<PT, true, 1> : kmc_lanes_kernel<PT, false, 1>);
+    // (the variants exist for the production instantiation only; the tracing one uses the defaults)
+    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 5, true> : kmc_lanes_kernel<PT, false, 3, MINB, PF>)
+              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 5, true> : kmc_lanes_kernel<PT, false, 2, MINB, PF>)
+                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 5, true> : kmc_lanes_kernel<PT, false, 1, MINB, PF>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 0, per_sm = 0;
@@ -516,6 +542,16 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
     kern<<<grid, warps * 32, smem, st>>>(L, E);
     if (launches) ++*launches;
     return cudaGetLastError();
+}
+
+template <int PT>
+static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
+    // experiment knobs (profiles/run_lanes.py): KMCB200_LANES_MINB = 5 | 6, KMCB200_LANES_PF = 0 | 1
+    int minb = LANES_MIN_CTAS, pf = 1;
+    if (const char *ev = getenv("KMCB200_LANES_MINB")) minb = atoi(ev);
+    if (const char *ev = getenv("KMCB200_LANES_PF")) pf = atoi(ev);
+    if (minb >= 6) return pf ? launch_lanes_v<PT, 6, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 6, false>(L, E, st, launches, plan_only);
+    return pf ? launch_lanes_v<PT, 5, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 5, false>(L, E, st, launches, plan_only);
 }
 
 // plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the table
