@@ -52,17 +52,16 @@ namespace kmcb200 {
 
 #define LENTB 256u  // bytes per table entry
 #ifndef LANES_MIN_CTAS
-#define LANES_MIN_CTAS 5  // resident CTAs of 4 warps per SM the register budget is set for
+#define LANES_MIN_CTAS 6  // resident CTAs of 4 warps per SM the register budget is set for
 #endif
 
 template <int PT>
 struct LanesGeom {
     static constexpr int PV = PT > 0 ? PT : 32;   // electrode slots per trajectory
     static constexpr int MIRB = 256;              // mirror: acceptor energies (128 B) | electrode energies (128 B)
-    static constexpr int EFB = 32 * 32 * 4;       // E_constant (the narrowed fp32 values) of the 32 trajectories
     static constexpr int VEB = 32 * PV * 4;       // electrode energies of the 32 trajectories
     static constexpr int TALB = PV * 32 * 4;      // electrode tallies [electrode][trajectory]
-    static constexpr int WARP_BYTES = MIRB + EFB + VEB + TALB;
+    static constexpr int WARP_BYTES = MIRB + VEB + TALB;
 };
 
 __device__ __forceinline__ uint4 ldg_u4(const unsigned char *p) {
@@ -101,6 +100,12 @@ __device__ __forceinline__ void stg_u4(unsigned char *p, uint4 v) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void stg_u32(unsigned char *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ float ldg_f32(const unsigned char *p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg_f32(unsigned char *p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void stg_u16(unsigned char *p, uint32_t v) {
     asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.global.u16 [%0], t; }" ::"l"(p), "r"(v) : "memory");
 }
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
-    const uint32_t a_mir = wb, a_ef = wb + G::MIRB, a_ve = a_ef + G::EFB, a_tal = a_ve + G::VEB;
+    const uint32_t a_mir = wb, a_ve = wb + G::MIRB, a_tal = a_ve + G::VEB;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
@@ -153,6 +158,9 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
     const int tlog = E.gtab_log;  // log2(table entries per warp slot), >= 6
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
     unsigned char *const wtab = E.gtab + ((size_t)wslot << tlog) * LENTB;
+    // E_constant of the warp's 32 trajectories, narrowed to float32 (row t, lane = acceptor): 4 KB per warp slot in
+    // global memory (read on evaluations only, L1 / L2 hits) -- shared memory is what limits the resident warps
+    unsigned char *const wef = E.lanes_scratch + (size_t)wslot * 4096 + lane * 4;
     const bool use_table = !(E.lanes_flags & 1);
     const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
     const int64_t total_hops = E.prehops + E.hops, prehops = E.prehops;
@@ -178,36 +186,34 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         uint32_t occ = 0;
         if (E.occupation0 && active)
             for (int i = 0; i < N; ++i) occ |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
-        // E_constant of every trajectory, narrowed to float32 (simulationWrapper.go:50-56): row t, lane = acceptor
-        for (int t = 0; t < 32; ++t) {
-            const int64_t mt = base + t;
-            float ef = 0.0f;
-            if (mt < E.B && lane < N) {
-                double E64;
-                if (E.E_constant) E64 = E.E_constant[mt * N + lane];
-                else {
-                    E64 = E.basis[(int64_t)P * N + lane];
-                    for (int p = 0; p < P; ++p) E64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
-                }
-                ef = (float)E64;
-            }
-            sts_f(a_ef + (uint32_t)(t * 32 + lane) * 4u, ef);
-        }
         __syncwarp();
-
-        // ---- runs of identical members: bit t of sp = member t has the parameters of member t-1
+        // E_constant of every trajectory, narrowed to float32 (simulationWrapper.go:50-56): row t, lane = acceptor;
+        // runs of identical members: bit t of sp = member t has the parameters of member t-1
         uint32_t sp = 0;
         {
-            const float nbp = __shfl_up_sync(FULL, nb, 1);
-            const uint32_t spk = __ballot_sync(FULL, !active || (lane > 0 && __float_as_uint(nbp) == __float_as_uint(nb)));
-            for (int t = 1; t < 32; ++t) {
-                bool eq = true;
-                if (lane < N) eq = lds_u(a_ef + (uint32_t)(t * 32 + lane) * 4u) == lds_u(a_ef + (uint32_t)((t - 1) * 32 + lane) * 4u);
-                if (lane < P) eq = eq && lds_u(a_ve + (uint32_t)(t * PV + lane) * 4u) == lds_u(a_ve + (uint32_t)((t - 1) * PV + lane) * 4u);
-                if (__all_sync(FULL, eq) || base + t >= E.B) sp |= 1u << t;
+            float prev = 0.0f;
+            for (int t = 0; t < 32; ++t) {
+                const int64_t mt = base + t;
+                float ef = 0.0f;
+                if (mt < E.B && lane < N) {
+                    double E64;
+                    if (E.E_constant) E64 = E.E_constant[mt * N + lane];
+                    else {
+                        E64 = E.basis[(int64_t)P * N + lane];
+                        for (int p = 0; p < P; ++p) E64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
+                    }
+                    ef = (float)E64;
+                }
+                stg_f32(wef + t * 128, ef);
+                bool eq = __float_as_uint(ef) == __float_as_uint(prev);
+                if (lane < P && t > 0) eq = eq && lds_u(a_ve + (uint32_t)(t * PV + lane) * 4u) == lds_u(a_ve + (uint32_t)((t - 1) * PV + lane) * 4u);
+                if (t > 0 && (__all_sync(FULL, eq) || mt >= E.B)) sp |= 1u << t;
+                prev = ef;
             }
-            sp &= spk;
+            const float nbp = __shfl_up_sync(FULL, nb, 1);
+            sp &= __ballot_sync(FULL, !active || (lane > 0 && __float_as_uint(nbp) == __float_as_uint(nb)));
         }
+        __syncwarp();
         int glog = 0;  // log2(run length): the largest aligned power of two such that every run is uniform
         if ((sp | 0x00000001u) == FULL) glog = 5;
         else if ((sp | 0x00010001u) == FULL) glog = 4;
@@ -291,7 +297,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 const float nbt = __shfl_sync(FULL, nb, t);
                 const uint32_t xt = __shfl_sync(FULL, xr, t);
-                const double E64 = (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u);
+                const double E64 = (double)ldg_f32(wef + t * 128);
                 float ve_mine = 0.0f;  // electrode `lane` of trajectory t
                 __syncwarp();
                 if (lane < P) {
@@ -506,7 +512,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 if (mt >= E.B) continue;
                 if (lane < N)
-                    E.site_energies_out[mt * S + lane] = energy_of(occu, accm, (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u), a_row_me);
+                    E.site_energies_out[mt * S + lane] = energy_of(occu, accm, (double)ldg_f32(wef + t * 128), a_row_me);
                 if (lane < P) E.site_energies_out[mt * S + N + lane] = (double)lds_f(a_ve + (uint32_t)(t * PV + lane) * 4u);
             }
         }
@@ -522,9 +528,9 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
     // (the variants exist for the production instantiation only; the tracing one uses the defaults)
-    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 5, true> : kmc_lanes_kernel<PT, false, 3, MINB, PF>)
-              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 5, true> : kmc_lanes_kernel<PT, false, 2, MINB, PF>)
-                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 5, true> : kmc_lanes_kernel<PT, false, 1, MINB, PF>);
+    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 6, false> : kmc_lanes_kernel<PT, false, 3, MINB, PF>)
+              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 6, false> : kmc_lanes_kernel<PT, false, 2, MINB, PF>)
+                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 6, false> : kmc_lanes_kernel<PT, false, 1, MINB, PF>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 0, per_sm = 0;
@@ -547,9 +553,11 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
 template <int PT>
 static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     // experiment knobs (profiles/run_lanes.py): KMCB200_LANES_MINB = 5 | 6, KMCB200_LANES_PF = 0 | 1
-    int minb = LANES_MIN_CTAS, pf = 1;
+    int minb = LANES_MIN_CTAS, pf = 0;
     if (const char *ev = getenv("KMCB200_LANES_MINB")) minb = atoi(ev);
     if (const char *ev = getenv("KMCB200_LANES_PF")) pf = atoi(ev);
+    if (minb >= 8) return launch_lanes_v<PT, 8, false>(L, E, st, launches, plan_only);
+    if (minb == 7) return launch_lanes_v<PT, 7, false>(L, E, st, launches, plan_only);
     if (minb >= 6) return pf ? launch_lanes_v<PT, 6, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 6, false>(L, E, st, launches, plan_only);
     return pf ? launch_lanes_v<PT, 5, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 5, false>(L, E, st, launches, plan_only);
 }
