@@ -25,9 +25,10 @@
 // occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset:
 //
 //     0   u32 key | f32 1/total | u32 launch id | u32 first member of the run + 1
-//     16 + 64c   8 x u32   thresholds of events 8c .. 8c+7: inclusive cumulative rate / total in 0.32 fixed point
-//     48 + 64c   8 x u16   their codes: event (partner acceptor j | 32+e hole into electrode e | 64+e hole out of
-//                          electrode e) | acceptor << 7                                         (c = 0 .. 3)
+//     16 + 64c   8 x u16   codes of events 8c .. 8c+7: event (partner acceptor j | 32+e hole into electrode e | 64+e
+//                          hole out of electrode e) | acceptor << 7
+//     32 + 64c   8 x u32   their thresholds: inclusive cumulative rate / total in 0.32 fixed point   (c = 0 .. 3)
+//   (the first chunk is read with two 256-bit loads: header + codes, thresholds)
 //
 // The events are the 31 event slots of hop_memo.cu (every acceptor's largest rates), SORTED by decreasing rate: on C3
 // the first chunk answers most hops with one 48-byte read.  The pick compares the raw 32-bit Philox output x against
@@ -59,9 +60,10 @@ template <int PT>
 struct LanesGeom {
     static constexpr int PV = PT > 0 ? PT : 32;   // electrode slots per trajectory
     static constexpr int MIRB = 256;              // mirror: acceptor energies (128 B) | electrode energies (128 B)
+    static constexpr int EFB = 32 * 32 * 4;       // E_constant (the narrowed fp32 values) of the 32 trajectories
     static constexpr int VEB = 32 * PV * 4;       // electrode energies of the 32 trajectories
     static constexpr int TALB = PV * 32 * 4;      // electrode tallies [electrode][trajectory]
-    static constexpr int WARP_BYTES = MIRB + VEB + TALB;
+    static constexpr int WARP_BYTES = MIRB + EFB + VEB + TALB;
 };
 
 __device__ __forceinline__ uint4 ldg_u4(const unsigned char *p) {
@@ -69,25 +71,22 @@ __device__ __forceinline__ uint4 ldg_u4(const unsigned char *p) {
     asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-// header + first chunk (thresholds, codes; 64 B) in ONE statement: the loads are issued back to back, one latency
-__device__ __forceinline__ void ldg_head(const unsigned char *p, uint4 &h, uint4 &a, uint4 &b, uint4 &c) {
+// header + first chunk (codes, thresholds; 64 B) in ONE statement of two 256-bit loads, issued back to back
+__device__ __forceinline__ void ldg_head(const unsigned char *p, uint4 &h, uint4 &c, uint4 &a, uint4 &b) {
     asm volatile(
-        "ld.global.v4.u32 {%0, %1, %2, %3}, [%16];\n\t"
-        "ld.global.v4.u32 {%4, %5, %6, %7}, [%16+16];\n\t"
-        "ld.global.v4.u32 {%8, %9, %10, %11}, [%16+32];\n\t"
-        "ld.global.v4.u32 {%12, %13, %14, %15}, [%16+48];"
-        : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w),
-          "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+        "ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
+        "ld.global.v8.u32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%16+32];"
+        : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w),
+          "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
         : "l"(p)
         : "memory");
 }
-// thresholds + codes of a later chunk (48 B at p)
-__device__ __forceinline__ void ldg_chunk(const unsigned char *p, uint4 &a, uint4 &b, uint4 &c) {
+// codes + thresholds of a later chunk (48 B at p = entry + 64 c + 16)
+__device__ __forceinline__ void ldg_chunk(const unsigned char *p, uint4 &c, uint4 &a, uint4 &b) {
     asm volatile(
         "ld.global.v4.u32 {%0, %1, %2, %3}, [%12];\n\t"
-        "ld.global.v4.u32 {%4, %5, %6, %7}, [%12+16];\n\t"
-        "ld.global.v4.u32 {%8, %9, %10, %11}, [%12+32];"
-        : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w)
+        "ld.global.v8.u32 {%4, %5, %6, %7, %8, %9, %10, %11}, [%12+16];"
+        : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
         : "l"(p)
         : "memory");
 }
@@ -100,12 +99,6 @@ __device__ __forceinline__ void stg_u4(unsigned char *p, uint4 v) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void stg_u32(unsigned char *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ float ldg_f32(const unsigned char *p) {
-    float v;
-    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stg_f32(unsigned char *p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void stg_u16(unsigned char *p, uint32_t v) {
     asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.global.u16 [%0], t; }" ::"l"(p), "r"(v) : "memory");
 }
@@ -139,7 +132,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
-    const uint32_t a_mir = wb, a_ve = wb + G::MIRB, a_tal = a_ve + G::VEB;
+    const uint32_t a_mir = wb, a_ef = wb + G::MIRB, a_ve = a_ef + G::EFB, a_tal = a_ve + G::VEB;
     const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
     const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
     const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
@@ -158,9 +151,6 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
     const int tlog = E.gtab_log;  // log2(table entries per warp slot), >= 6
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
     unsigned char *const wtab = E.gtab + ((size_t)wslot << tlog) * LENTB;
-    // E_constant of the warp's 32 trajectories, narrowed to float32 (row t, lane = acceptor): 4 KB per warp slot in
-    // global memory (read on evaluations only, L1 / L2 hits) -- shared memory is what limits the resident warps
-    unsigned char *const wef = E.lanes_scratch + (size_t)wslot * 4096 + lane * 4;
     const bool use_table = !(E.lanes_flags & 1);
     const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
     const int64_t total_hops = E.prehops + E.hops, prehops = E.prehops;
@@ -186,34 +176,36 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         uint32_t occ = 0;
         if (E.occupation0 && active)
             for (int i = 0; i < N; ++i) occ |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
-        __syncwarp();
-        // E_constant of every trajectory, narrowed to float32 (simulationWrapper.go:50-56): row t, lane = acceptor;
-        // runs of identical members: bit t of sp = member t has the parameters of member t-1
-        uint32_t sp = 0;
-        {
-            float prev = 0.0f;
-            for (int t = 0; t < 32; ++t) {
-                const int64_t mt = base + t;
-                float ef = 0.0f;
-                if (mt < E.B && lane < N) {
-                    double E64;
-                    if (E.E_constant) E64 = E.E_constant[mt * N + lane];
-                    else {
-                        E64 = E.basis[(int64_t)P * N + lane];
-                        for (int p = 0; p < P; ++p) E64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
-                    }
-                    ef = (float)E64;
+        // E_constant of every trajectory, narrowed to float32 (simulationWrapper.go:50-56): row t, lane = acceptor
+        for (int t = 0; t < 32; ++t) {
+            const int64_t mt = base + t;
+            float ef = 0.0f;
+            if (mt < E.B && lane < N) {
+                double E64;
+                if (E.E_constant) E64 = E.E_constant[mt * N + lane];
+                else {
+                    E64 = E.basis[(int64_t)P * N + lane];
+                    for (int p = 0; p < P; ++p) E64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
                 }
-                stg_f32(wef + t * 128, ef);
-                bool eq = __float_as_uint(ef) == __float_as_uint(prev);
-                if (lane < P && t > 0) eq = eq && lds_u(a_ve + (uint32_t)(t * PV + lane) * 4u) == lds_u(a_ve + (uint32_t)((t - 1) * PV + lane) * 4u);
-                if (t > 0 && (__all_sync(FULL, eq) || mt >= E.B)) sp |= 1u << t;
-                prev = ef;
+                ef = (float)E64;
             }
-            const float nbp = __shfl_up_sync(FULL, nb, 1);
-            sp &= __ballot_sync(FULL, !active || (lane > 0 && __float_as_uint(nbp) == __float_as_uint(nb)));
+            sts_f(a_ef + (uint32_t)(t * 32 + lane) * 4u, ef);
         }
         __syncwarp();
+
+        // ---- runs of identical members: bit t of sp = member t has the parameters of member t-1
+        uint32_t sp = 0;
+        {
+            const float nbp = __shfl_up_sync(FULL, nb, 1);
+            const uint32_t spk = __ballot_sync(FULL, !active || (lane > 0 && __float_as_uint(nbp) == __float_as_uint(nb)));
+            for (int t = 1; t < 32; ++t) {
+                bool eq = true;
+                if (lane < N) eq = lds_u(a_ef + (uint32_t)(t * 32 + lane) * 4u) == lds_u(a_ef + (uint32_t)((t - 1) * 32 + lane) * 4u);
+                if (lane < P) eq = eq && lds_u(a_ve + (uint32_t)(t * PV + lane) * 4u) == lds_u(a_ve + (uint32_t)((t - 1) * PV + lane) * 4u);
+                if (__all_sync(FULL, eq) || base + t >= E.B) sp |= 1u << t;
+            }
+            sp &= spk;
+        }
         int glog = 0;  // log2(run length): the largest aligned power of two such that every run is uniform
         if ((sp | 0x00000001u) == FULL) glog = 5;
         else if ((sp | 0x00010001u) == FULL) glog = 4;
@@ -233,7 +225,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         long long n_miss = 0;
         uint4 r = make_uint4(0u, 0u, 0u, 0u);
         uint4 hd = make_uint4(0u, 0u, 0u, 0u), ta = hd, tb = hd, tc = hd;  // (launch ids start at 1: never a valid header)
-        if (PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, ta, tb, tc);
+        if (PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, tc, ta, tb);
 
         for (int64_t h = 0; h < total_hops; ++h) {
             if (h == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
@@ -261,7 +253,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
             uint32_t code = 0;
             float rt = 0.0f;
             bool hit = false, slow = false;
-            if (!PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, ta, tb, tc);
+            if (!PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, tc, ta, tb);
             // (thresholds never decrease: the last clause is always true for a valid entry -- it keeps ptxas from
             //  sinking the threshold loads below the branch, which would cost a second round trip)
             hit = alive && use_table && hd.x == occ && hd.z == tagx && hd.w == tagy && tb.w >= ta.x;
@@ -280,7 +272,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                         slow = true;
                         break;
                     }
-                    ldg_chunk(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB + (uint32_t)c * 64u + 16u, ta, tb, tc);
+                    ldg_chunk(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB + (uint32_t)c * 64u + 16u, tc, ta, tb);
                 }
             }
 
@@ -297,7 +289,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 const float nbt = __shfl_sync(FULL, nb, t);
                 const uint32_t xt = __shfl_sync(FULL, xr, t);
-                const double E64 = (double)ldg_f32(wef + t * 128);
+                const double E64 = (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u);
                 float ve_mine = 0.0f;  // electrode `lane` of trajectory t
                 __syncwarp();
                 if (lane < P) {
@@ -365,8 +357,8 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                         const uint32_t tagy_t = __shfl_sync(FULL, tagy, t);
                         unsigned char *ent = (unsigned char *)tb_t + (size_t)((occu * 0x9E3779B1u) >> hshift) * LENTB;
                         unsigned char *ch = ent + (uint32_t)(lane >> 3) * 64u;
-                        stg_u32(ch + 16 + (lane & 7) * 4, thr);
-                        stg_u16(ch + 48 + (lane & 7) * 2, scode);
+                        stg_u32(ch + 32 + (lane & 7) * 4, thr);
+                        stg_u16(ch + 16 + (lane & 7) * 2, scode);
                         if (lane == 0) stg_u4(ent, make_uint4(occu, __float_as_uint(rtot), tagx, tagy_t));
                         __syncwarp();
                     }
@@ -491,7 +483,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     tp[0] = from;
                     tp[1] = to;
                 }
-                if (PF && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, ta, tb, tc);
+                if (PF && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, tc, ta, tb);
             }
         }
 
@@ -512,7 +504,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 if (mt >= E.B) continue;
                 if (lane < N)
-                    E.site_energies_out[mt * S + lane] = energy_of(occu, accm, (double)ldg_f32(wef + t * 128), a_row_me);
+                    E.site_energies_out[mt * S + lane] = energy_of(occu, accm, (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u), a_row_me);
                 if (lane < P) E.site_energies_out[mt * S + N + lane] = (double)lds_f(a_ve + (uint32_t)(t * PV + lane) * 4u);
             }
         }
@@ -556,8 +548,6 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
     int minb = LANES_MIN_CTAS, pf = 0;
     if (const char *ev = getenv("KMCB200_LANES_MINB")) minb = atoi(ev);
     if (const char *ev = getenv("KMCB200_LANES_PF")) pf = atoi(ev);
-    if (minb >= 8) return launch_lanes_v<PT, 8, false>(L, E, st, launches, plan_only);
-    if (minb == 7) return launch_lanes_v<PT, 7, false>(L, E, st, launches, plan_only);
     if (minb >= 6) return pf ? launch_lanes_v<PT, 6, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 6, false>(L, E, st, launches, plan_only);
     return pf ? launch_lanes_v<PT, 5, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 5, false>(L, E, st, launches, plan_only);
 }

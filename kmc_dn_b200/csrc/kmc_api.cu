@@ -54,8 +54,6 @@ struct kmcb200_layout {
     void *ltab = nullptr;
     size_t ltab_bytes = 0;
     uint32_t lanes_launch_id = 0;
-    void *lscratch = nullptr;  // 4 KB per warp slot of that kernel
-    size_t lscratch_bytes = 0;
     unsigned long long *queue = nullptr;  // member work queue of the persistent kernel
     std::mutex mu;
 };
@@ -176,7 +174,6 @@ extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     cudaFree(lay->ws);
     cudaFree(lay->gtab);
     cudaFree(lay->ltab);
-    cudaFree(lay->lscratch);
     cudaFree(lay->queue);
     delete lay;
 }
@@ -338,18 +335,6 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         if (lanes) {
             E.lanes_flags = (a->flags & KMCB200_FLAG_NO_MEMO) ? 1 : 0;
             E.gtab = nullptr; E.gtab_log = 6;
-            {
-                MemoPlan plan{0};
-                le = launch_lanes(D, E, st, nullptr, &plan);
-                if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-                const size_t sbytes = (size_t)plan.warp_slots * 4096;
-                if (sbytes > lay->lscratch_bytes) {
-                    if (lay->lscratch) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->lscratch)); lay->lscratch = nullptr; lay->lscratch_bytes = 0; }
-                    CU(cudaMalloc(&lay->lscratch, sbytes));
-                    lay->lscratch_bytes = sbytes;
-                }
-                E.lanes_scratch = (unsigned char *)lay->lscratch;
-            }
             if (!(E.lanes_flags & 1)) {
                 // table entries per warp slot (shared by the warp's runs of identical members: a run of g gets g/32 of them)
                 int tlog = th < 3000 ? 11 : (th < 30000 ? 13 : 14);

@@ -43,7 +43,6 @@ struct EnsembleDev {
     unsigned long long *queue;  // memoised kernel: member work queue (zeroed before the launch)
     unsigned char *gtab;  // memoised kernels: second-level cache, warp_slots * 2^gtab_log entries of 288 / 448 B (or null)
     int gtab_log;         // log2(entries per warp slot); 0 = no second level
-    unsigned char *lanes_scratch;  // hop_lanes.cu: 4 KB per persistent warp slot (E_constant rows of its 32 trajectories)
     int lanes_flags;      // hop_lanes.cu: bit 0 = do not consult the table (every hop is evaluated; for testing)
     uint32_t launch_id;   // entries are valid only with the tag (launch_id, member + 1): the table is zeroed ONCE, at
                           // allocation, and never reset -- neither per launch nor per member
