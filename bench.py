@@ -179,7 +179,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from kmc_dn_b200.ensemble import Layout, launch_count
+    from kmc_dn_b200.ensemble import Layout, launch_count, last_kernel
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -251,6 +251,7 @@ def main():
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = launch_count() - l0
+    kernel = last_kernel().replace("kmc_", "").replace("_kernel", "")  # lanes | memo | wide
     ms = sum(a.elapsed_time(b) for a, b in ev)
     clocks = sampler.stop()
     tsum = float(time_d.sum().item())
@@ -293,9 +294,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         "ms_per_step": e2e_ms / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall}
-        stats = sample_statistics(lay, w, lt, member0)
-        line["roofline"] = roofline(value / world, ms / args.steps, B, hops, lt, stats, lay, local,
-                                    "wide" if lt.N > 31 else "memo")
+        stats = sample_statistics(lay, w, lt, member0, kernel)
+        line["roofline"] = roofline(value / world, ms / args.steps, B, hops, lt, stats, lay, local, kernel)
         if world == 1 and not args.no_cpu_baseline:
             s = cpu_sample(w, args.cpu_seconds)
             s_nc = cpu_sample(w, args.cpu_seconds / 3, use_cache=False)
@@ -327,15 +327,20 @@ def lay_run_host(lay, B, hops, kT, V, basis, occ0, time_out, eo_out, seed, membe
         raise RuntimeError(_lib.last_error())
 
 
-def sample_statistics(lay, w, lt, member0, n_sample=4096):
+def sample_statistics(lay, w, lt, member0, kernel="memo", n_sample=4096):
     """One small DBG launch on a strided subset of the ensemble: cache hit rate and mean hole count, from which the
-    algorithmic pair count A = n_h*(N-n_h) + N*P of SURVEY.md 8(d) follows."""
+    algorithmic pair count A = n_h*(N-n_h) + N*P of SURVEY.md 8(d) follows.  For the thread-per-trajectory kernel the
+    rate of state evaluations is taken from a launch of THAT kernel on a contiguous block of members (its tables are
+    shared by the consecutive seeds of a voltage vector, which a strided subset would tear apart)."""
     n_sample = min(n_sample, len(w["V"]))
     idx = np.linspace(0, len(w["V"]) - 1, n_sample).astype(np.int64)
     r = lay.run(w["hops"], w["kT"][idx], w["V"][idx], basis=lt.basis, occupation0=w["occupation0"], seed=7,
                 member_index0=member0, record=True, want_misses=True)
     nh = (r["avg_occupation"] / r["time"][:, None]).sum(1)
     A = float(np.mean(nh * (lt.N - nh) + lt.N * lt.P))
+    if kernel == "lanes":
+        r = lay.run(w["hops"], w["kT"][:n_sample], w["V"][:n_sample], basis=lt.basis, occupation0=w["occupation0"], seed=7,
+                    member_index0=member0, want_misses=True, kernel="lanes")
     return {"members": int(n_sample), "miss_rate": float(r["misses"].mean() / w["hops"]), "mean_holes": float(nh.mean()),
             "pairs_per_hop_A": A, "pairs_per_hop_A_nominal": lt.N * (lt.N - 1) + 2 * lt.N * lt.P}
 
@@ -370,8 +375,10 @@ def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device, kerne
             "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s", "frac": achieved / issue_peak if achieved else None,
             "peak_source": "dependent-free IADD micro-kernel on this device (kmcb200_measure_peak); nominal 148 SM x 4/clk",
             "work_per_hop": {"warp_inst": wih, "ncu_issue_active_pct": ncu.get("issue_active_pct"), "source": ncu.get("source"),
-                             "note": "instructions executed per hop (hit path 27 + amortised misses / variate refills), from "
-                                     "the committed ncu capture of this kernel on this workload (profiles/)"},
+                             "note": ("instructions executed per hop and trajectory (per-thread table hits ~5.5 + amortised "
+                                      "warp-cooperative state evaluations), " if kernel == "lanes" else
+                                      "instructions executed per hop (hit path 27 + amortised misses / variate refills), ") +
+                                     "from the committed ncu capture of this kernel on this workload (profiles/)"},
             "sfu_algorithmic": {"achieved": alg / 1e9, "peak": ex2_peak / 1e9, "unit": "Gexp/s", "frac": alg / ex2_peak,
                                 "executed_frac": executed / ex2_peak,
                                 "note": "SURVEY 8(d): hops/s x A against the MUFU.EX2 peak measured on this device; > 1 means "
@@ -383,8 +390,8 @@ def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device, kerne
                         if "dram_bytes_read_per_member" in ncu else None),
             "traffic_note": "dram__bytes_read+write of the ncu capture, scaled per member to this launch.  Algorithmic "
                             f"bytes per member = {bytes_per_member} (inputs {8 * lt.P + 8 + lt.N} B, outputs {8 + 8 * lt.P} B); the rest "
-                            "is the second-level state cache (warp slots x 256 entries x 272 B > L2) spilling to HBM -- "
-                            "working set by design, ~2 % of the HBM bandwidth",
+                            "is the state table / second-level state cache (a few hundred 256-288 B entries per run of "
+                            "trajectories, > L2 in total) spilling to HBM -- working set by design, ~2 % of the HBM bandwidth",
             "sample": stats}
 
 

@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         const int hshift = 32 - slog;
         const uint32_t grp = (uint32_t)lane >> glog;
         unsigned char *const tbase = wtab + ((size_t)grp << slog) * LENTB;
+        const uint32_t gofs = (grp << slog) * LENTB;  // (byte offsets inside a warp slot's table fit 32 bits: <= 2^16 entries)
+#define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
         const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
 
         const uint64_t gm = E.member_index0 + (uint64_t)mc;
@@ -225,21 +227,29 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         long long n_miss = 0;
         uint4 r = make_uint4(0u, 0u, 0u, 0u);
         uint4 hd = make_uint4(0u, 0u, 0u, 0u), ta = hd, tb = hd, tc = hd;  // (launch ids start at 1: never a valid header)
-        if (PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, tc, ta, tb);
+        if (PF && alive && use_table) ldg_head(LANES_ENT(occ), hd, tc, ta, tb);
 
-        for (int64_t h = 0; h < total_hops; ++h) {
-            if (h == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
+        // segments: a segment never straddles a 64-hop variate block or the prehops boundary
+        bool stop = false;
+        for (int64_t h0 = 0; h0 < total_hops && !stop;) {
+            if (h0 == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
                 t_acc = 0.0;
                 t_part = 0.0f;
                 for (int e = 0; e < P; ++e) sts_u(a_tal + (uint32_t)e * 128u + lane * 4u, 0u);
-            } else if ((h & 63) == 0) {
+            } else {
                 t_acc += (double)t_part;
                 t_part = 0.0f;
             }
+            int64_t hend = (h0 | 63) + 1;
+            if (hend > total_hops) hend = total_hops;
+            if (h0 < prehops && hend > prehops) hend = prehops;
+            const int q0 = (int)(h0 & 63), q1 = q0 + (int)(hend - h0);
+            const uint64_t blk0 = (uint64_t)(h0 >> 6) * 32u;
+            for (int q = q0; q < q1; ++q) {
             // ---- random variates: unit exponential for the dwell time (simulation.go:297), 32 uniform bits for the pick (:164)
             uint32_t xr, er;
-            if (!(h & 1)) {
-                const uint64_t blk = (uint64_t)(h >> 6) * 32u + (uint64_t)((h & 63) >> 1);
+            if (!(q & 1)) {
+                const uint64_t blk = blk0 + (uint64_t)(q >> 1);
                 r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), key);
                 er = r.x;
                 xr = r.y;
@@ -253,7 +263,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
             uint32_t code = 0;
             float rt = 0.0f;
             bool hit = false, slow = false;
-            if (!PF && alive && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, tc, ta, tb);
+            if (!PF && alive && use_table) ldg_head(LANES_ENT(occ), hd, tc, ta, tb);
             // (thresholds never decrease: the last clause is always true for a valid entry -- it keeps ptxas from
             //  sinking the threshold loads below the branch, which would cost a second round trip)
             hit = alive && use_table && hd.x == occ && hd.z == tagx && hd.w == tagy && tb.w >= ta.x;
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                         slow = true;
                         break;
                     }
-                    ldg_chunk(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB + (uint32_t)c * 64u + 16u, tc, ta, tb);
+                    ldg_chunk(LANES_ENT(occ) + (uint32_t)c * 64u + 16u, tc, ta, tb);
                 }
             }
 
@@ -316,13 +326,9 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     if (sl_r >= NR) sv = 0.0f;
                 }
                 if (lane == 31) sv = 0.0f;
-                double mtop = (double)sv, rsum = (double)rest_tot;
+                double total = (double)sv + (double)rest_tot;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    mtop += __shfl_xor_sync(FULL, mtop, d);
-                    rsum += __shfl_xor_sync(FULL, rsum, d);
-                }
-                const double total = mtop + rsum;
+                for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
                 if (!(total > 0.0)) {  // no transition possible (simulation.go:297 would divide by zero)
                     if (lane == t) { alive = false; dead = true; }
                     died = true;
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     if (use_table) {
                         const unsigned long long tb_t = __shfl_sync(FULL, (unsigned long long)tbase, t);
                         const uint32_t tagy_t = __shfl_sync(FULL, tagy, t);
-                        unsigned char *ent = (unsigned char *)tb_t + (size_t)((occu * 0x9E3779B1u) >> hshift) * LENTB;
+                        unsigned char *ent = (unsigned char *)tb_t + (size_t)(((occu * 0x9E3779B1u) >> hshift) * LENTB);
                         unsigned char *ch = ent + (uint32_t)(lane >> 3) * 64u;
                         stg_u32(ch + 32 + (lane & 7) * 4, thr);
                         stg_u16(ch + 16 + (lane & 7) * 2, scode);
@@ -384,6 +390,9 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     int sk[NR];
 #pragma unroll
                     for (int rr = 0; rr < NR; ++rr) sk[rr] = (rr < n_slots && tk[rr] > 0.0f) ? pk[rr] : -1;
+                    double mtop = (double)sv;  // mass of the slot events
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) mtop += __shfl_xor_sync(FULL, mtop, d);
                     const double rres = ((double)xt + 0.5) * 2.3283064365386963e-10 * total - mtop;
                     const double incl = scan_d((double)rest_tot);
                     double ex = __shfl_up_sync(FULL, incl, 1);
@@ -462,7 +471,10 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     if (lane == t) code = rcode;
                 }
             }
-            if (died && !__any_sync(FULL, alive)) break;
+            if (died && !__any_sync(FULL, alive)) {
+                stop = true;
+                break;
+            }
 
             // ---- step 4: apply (simulation.go:107-130, 306-319): the slot's acceptor flips; an acceptor partner flips
             //      too; an electrode partner gains (32+e) or loses (64+e) one hole
@@ -474,17 +486,19 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     sts_u(a, lds_u(a) + (evt < 64u ? 1u : 0xffffffffu));
                 }
                 t_part = fmaf(ek, rt, t_part);
-                if (DBG && E.trace && h >= prehops) {
+                if (DBG && E.trace && h0 >= prehops) {
                     int from, to;
                     if (evt < 32u) { from = (int)site; to = (int)evt; }
                     else if (evt < 64u) { from = (int)site; to = N + (int)evt - 32; }
                     else { from = N + (int)evt - 64; to = (int)site; }
-                    int32_t *tp = E.trace + (m * E.hops + (h - prehops)) * 2;
+                    int32_t *tp = E.trace + (m * E.hops + (h0 + (q - q0) - prehops)) * 2;
                     tp[0] = from;
                     tp[1] = to;
                 }
-                if (PF && use_table) ldg_head(tbase + (size_t)((occ * 0x9E3779B1u) >> hshift) * LENTB, hd, tc, ta, tb);
+                if (PF && use_table) ldg_head(LANES_ENT(occ), hd, tc, ta, tb);
             }
+            }  // hops of the segment
+            h0 = hend;
         }
 
         // ---- results
@@ -520,9 +534,9 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
     // (the variants exist for the production instantiation only; the tracing one uses the defaults)
-    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 6, false> : kmc_lanes_kernel<PT, false, 3, MINB, PF>)
-              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 6, false> : kmc_lanes_kernel<PT, false, 2, MINB, PF>)
-                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 6, false> : kmc_lanes_kernel<PT, false, 1, MINB, PF>);
+    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 6, true> : kmc_lanes_kernel<PT, false, 3, MINB, PF>)
+              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 6, true> : kmc_lanes_kernel<PT, false, 2, MINB, PF>)
+                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 6, true> : kmc_lanes_kernel<PT, false, 1, MINB, PF>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 0, per_sm = 0;
@@ -545,7 +559,7 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
 template <int PT>
 static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     // experiment knobs (profiles/run_lanes.py): KMCB200_LANES_MINB = 5 | 6, KMCB200_LANES_PF = 0 | 1
-    int minb = LANES_MIN_CTAS, pf = 0;
+    int minb = LANES_MIN_CTAS, pf = 1;
     if (const char *ev = getenv("KMCB200_LANES_MINB")) minb = atoi(ev);
     if (const char *ev = getenv("KMCB200_LANES_PF")) pf = atoi(ev);
     if (minb >= 6) return pf ? launch_lanes_v<PT, 6, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 6, false>(L, E, st, launches, plan_only);

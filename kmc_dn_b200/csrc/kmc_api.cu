@@ -71,6 +71,8 @@ extern "C" void kmcb200_set_seed(uint64_t seed) {
     g_next_member.store(0);
 }
 extern "C" long long kmcb200_launch_count(void) { return g_launches.load(); }
+static thread_local const char *g_last_kernel = "";
+extern "C" const char *kmcb200_last_kernel(void) { return g_last_kernel; }
 extern "C" double kmcb200_measure_peak(int device, int what) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     int launches = 0;
@@ -192,7 +194,7 @@ size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 }  // namespace
 
 // MODE_FAST, N <= 31: ensembles of at least this many members run on the thread-per-trajectory kernel (hop_lanes.cu)
-static const int64_t kLanesAutoMinB = INT64_MAX;
+static const int64_t kLanesAutoMinB = 32768;
 
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");
@@ -308,9 +310,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
 
     int launches = 0;
     cudaError_t le;
-    if (prob) le = launch_prob(D, E, st, &launches);
-    else if (exact) le = launch_exact(D, E, st, &launches);
-    else if (a->mode == KMCB200_MODE_FAST_REFORDER) le = launch_reforder(D, E, st, &launches);
+    if (prob) { le = launch_prob(D, E, st, &launches); g_last_kernel = "kmc_prob_kernel"; }
+    else if (exact) { le = launch_exact(D, E, st, &launches); g_last_kernel = "kmc_exact_kernel"; }
+    else if (a->mode == KMCB200_MODE_FAST_REFORDER) { le = launch_reforder(D, E, st, &launches); g_last_kernel = "kmc_reforder_kernel"; }
     else if (!getenv("KMCB200_NO_MEMO_KERNEL")) {
         // memoised production kernels: hop_lanes.cu (N <= 31, large ensembles: one thread per trajectory on the hit path),
         // hop_memo.cu (N <= 31: one warp per trajectory, one mask word, sentinel lane) / hop_wide.cu (N <= 256)
@@ -337,7 +339,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             E.gtab = nullptr; E.gtab_log = 6;
             if (!(E.lanes_flags & 1)) {
                 // table entries per warp slot (shared by the warp's runs of identical members: a run of g gets g/32 of them)
-                int tlog = th < 3000 ? 11 : (th < 30000 ? 13 : 14);
+                int tlog = th < 3000 ? 12 : 14;
                 if (const char *ev = getenv("KMCB200_LTAB_LOG")) tlog = atoi(ev);
                 if (tlog < 6) tlog = 6;
                 if (tlog > 16) tlog = 16;
@@ -370,8 +372,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                 else lanes = false;
             }
         }
-        if (lanes) le = launch_lanes(D, E, st, &launches);
+        if (lanes) { le = launch_lanes(D, E, st, &launches); g_last_kernel = "kmc_lanes_kernel"; }
         else {
+        g_last_kernel = narrow ? "kmc_memo_kernel" : "kmc_wide_kernel";
         // second-level entries per warp slot: enough that a trajectory's few hundred states rarely collide in the
         // direct-mapped table (conflict misses: 1.5 % of the hops at 256 entries, 0.1 % at 1024 on a 1e6-hop C3 member)
         // first-level entries per warp: 16 when the SMs are full of trajectories (shared memory is what limits the resident
@@ -413,7 +416,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         }
         le = narrow ? launch_memo(D, E, logk, st, &launches) : launch_wide(D, E, logk, st, &launches);
         }
-    } else le = launch_fast(D, E, st, &launches);
+    } else { le = launch_fast(D, E, st, &launches); g_last_kernel = "kmc_fast_kernel"; }
     g_launches += launches;
     if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));
 

@@ -183,6 +183,11 @@ class Layout:
         return se, rates
 
 
+def last_kernel():
+    """Name of the hop kernel this thread's last run launched (kmcb200_last_kernel)."""
+    return _lib.load().kmcb200_last_kernel().decode()
+
+
 def launch_count():
     return int(_lib.load().kmcb200_launch_count())
 

@@ -52,6 +52,7 @@ def main():
     ap.add_argument("--hops", type=int, default=10000)
     ap.add_argument("--tlogs", default="")
     ap.add_argument("--c4", action="store_true")
+    ap.add_argument("--crossover", default="", help="member counts at which both kernels are timed, e.g. 8192,16384,32768")
     ap.add_argument("--kernels", default="warp,lanes")
     ap.add_argument("--variants", default="", help="lanes kernel experiment knobs, e.g. 5:0,5:1,6:1 (min CTAs per SM : prefetch)")
     args = ap.parse_args()
@@ -74,6 +75,12 @@ def main():
                 print(json.dumps(r), flush=True)
             os.environ.pop("KMCB200_LTAB_LOG", None)
         os.environ.pop("KMCB200_LANES_MINB", None); os.environ.pop("KMCB200_LANES_PF", None)
+    for b in [int(x) for x in args.crossover.split(",") if x]:
+        wb = workloads.c3_voltage_search(n_controls=max(1, b // (4 * args.seeds)), seeds=args.seeds)
+        for k in ("warp", "lanes"):
+            r = measure(lay, lt, wb, args.hops, 0, k)
+            r["workload"] = "c3-crossover"
+            print(json.dumps(r), flush=True)
     lay.close()
     if args.c4:
         w = workloads.c4_temperature()

@@ -212,7 +212,7 @@ def test_fast_kernel_one_hop_event_distribution_matches_oracle_rates(golden_py, 
         p = r_o.astype(np.float64).ravel(); p /= p.sum()
         lay = _layout(c)
         r = lay.run(1, c["kT"], np.tile(c["electrode_v"], (B, 1)), E_constant=np.tile(c["E_constant"], (B, 1)),
-                    occupation0=c["occupation"], seed=77, trace=True)
+                    occupation0=c["occupation"], seed=77, trace=True, kernel="warp")  # (lanes kernel: tests/test_gpu_lanes.py)
         lay.close()
         ev = r["trace"][:, 0, 0].astype(np.int64) * S + r["trace"][:, 0, 1]
         cnt = np.bincount(ev, minlength=S * S).astype(np.float64)
