@@ -22,13 +22,16 @@
 // (the seeds of one voltage vector / temperature) SHARE one table: the warp detects aligned runs of 2..32 identical
 // members among its 32 and gives every run one direct-mapped table in global memory (hot entries live in L1 / L2; the
 // hardware caches replace the hand-managed first level of hop_memo.cu).  An entry (256 B) is keyed by the full
-// occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset:
+// occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset (512 B):
 //
 //     0   u32 key | f32 1/total | u32 launch id | u32 first member of the run + 1
 //     16 + 64c   8 x u16   codes of events 8c .. 8c+7: event (partner acceptor j | 32+e hole into electrode e | 64+e
 //                          hole out of electrode e) | acceptor << 7
 //     32 + 64c   8 x u32   their thresholds: inclusive cumulative rate / total in 0.32 fixed point   (c = 0 .. 3)
-//   (the first chunk is read with two 256-bit loads: header + codes, thresholds)
+//     64  f64 total rate | f64 mass of the slot events
+//     256 32 x f32  per acceptor: mass of its events outside the slots     384 32 x f32  per acceptor: site energy
+//   (the first chunk is read with two 256-bit loads: header + codes, thresholds; the second half of the entry serves
+//    the rest-of-list picks, so that they need no second evaluation of the state)
 //
 // The events are the 31 event slots of hop_memo.cu (every acceptor's largest rates), SORTED by decreasing rate: on C3
 // the first chunk answers most hops with one 48-byte read.  The pick compares the raw 32-bit Philox output x against
@@ -51,7 +54,7 @@
 
 namespace kmcb200 {
 
-#define LENTB 256u  // bytes per table entry
+#define LENTB 512u  // bytes per table entry
 #ifndef LANES_MIN_CTAS
 #define LANES_MIN_CTAS 6  // resident CTAs of 4 warps per SM the register budget is set for
 #endif
@@ -99,8 +102,96 @@ __device__ __forceinline__ void stg_u4(unsigned char *p, uint4 v) {
     asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void stg_u32(unsigned char *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ float ldg_f32(const unsigned char *p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ldg_f64(const unsigned char *p) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stg_f32(unsigned char *p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+__device__ __forceinline__ void stg_f64(unsigned char *p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 __device__ __forceinline__ void stg_u16(unsigned char *p, uint32_t v) {
     asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.global.u16 [%0], t; }" ::"l"(p), "r"(v) : "memory");
+}
+
+// The rest of the list: exact two-level pick over all events EXCEPT the ones that own a slot (x >= mass of the slot
+// events; hop_memo.cu's slow path).  Works on the state's per-acceptor data -- rest_tot (mass outside the slots), e_me
+// (fp32 site energy), code_l (ANY permutation of the slot codes: event | acceptor << 7 | valid << 12) -- either fresh
+// from a sweep or read back from the table entry: the result does not depend on which, nor on the order of the slots.
+// Warp-cooperative (lane = acceptor / target / electrode); returns the event code (event | acceptor << 7), warp-uniform.
+__device__ __noinline__ uint32_t slow_pick(uint32_t occu, uint32_t accm, float nbt, uint32_t x, double total, double mtop,
+                                              float rest_tot, float e_me, float ve_mine, uint32_t code_l, int lane, int N, int P,
+                                              uint32_t a_col_me, uint32_t a_elF_e, uint32_t a_elR_e) {
+    const double rres = ((double)x + 0.5) * 2.3283064365386963e-10 * total - mtop;
+    const double incl = scan_d((double)rest_tot);
+    double ex = __shfl_up_sync(FULL, incl, 1);
+    if (lane == 0) ex = 0.0;
+    const uint32_t rpos = __ballot_sync(FULL, rest_tot > 0.0f);
+    uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
+    if (!b2) b2 = rpos & (0u - rpos);
+    const bool valid = (code_l >> 12) & 1u;
+    const uint32_t c12 = code_l & 4095u;
+    // an event that is certainly allowed, for the cases rounding leaves without a pick
+    const uint32_t any_valid = __reduce_max_sync(FULL, valid ? c12 : 0u);
+    if (!b2) return any_valid;  // no mass outside the slots (rounding)
+    const int istar = 31 - __clz(b2);
+    const float rf = __shfl_sync(FULL, (float)(rres - ex), istar);
+    // the acceptor's events that own a slot are skipped; the smallest of their codes is the rounding fallback
+    const bool match = valid && (int)((code_l >> 7) & 31u) == istar;
+    const uint32_t evt = code_l & 127u;
+    const uint32_t skipA = __reduce_or_sync(FULL, (match && evt < 32u) ? (1u << evt) : 0u);
+    const uint32_t skipE = __reduce_or_sync(FULL, (match && evt >= 32u) ? (1u << (evt & 31u)) : 0u);
+    uint32_t fallback = __reduce_min_sync(FULL, match ? c12 : 0xffffu);
+    if (fallback == 0xffffu) fallback = any_valid;
+    const bool keepA = !((skipA >> lane) & 1u), keepE = !((skipE >> lane) & 1u);
+    const bool rowocc = (occu >> istar) & 1u;
+    const float e_star = __shfl_sync(FULL, e_me, istar);
+    int from, to;
+    if (rowocc) {
+        from = istar;
+        to = -1;
+        int lastA = -1;
+        float sA = 0.0f;
+        const uint32_t emp = ~occu & accm;
+        if (emp) {  // acceptor targets: istar -> empty `lane`
+            float rr = 0.0f;
+            if (((emp >> lane) & 1u) && keepA) {
+                const float2 v = lds_f2(a_col_me + istar * 8);
+                rr = ma(v.x, v.y, e_me, e_star, nbt);
+            }
+            const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
+            if (nz) {
+                const float sc = scan_f<5>(rr);
+                const uint32_t b3 = __ballot_sync(FULL, sc >= rf) & nz;
+                if (b3) to = __ffs(b3) - 1;
+                else {
+                    lastA = 31 - __clz(nz);
+                    sA = __shfl_sync(FULL, sc, 31);
+                }
+            }
+        }
+        if (to < 0) {  // electrode targets: istar -> electrode `lane`
+            float rr = 0.0f;
+            if (lane < P && keepE) rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nbt, 0.0f));
+            const int e = pick_group<5>(rr, rf - sA);
+            to = (e >= 0) ? N + e : lastA;
+        }
+        if (to < 0) return fallback;
+    } else {  // empty acceptor: events electrode `lane` -> istar
+        to = istar;
+        float rr = 0.0f;
+        if (lane < P && keepE) rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nbt, 0.0f));
+        from = pick_group<5>(rr, rf);
+        if (from < 0) return fallback;
+        from += N;
+    }
+    if (from < N && to < N) return (uint32_t)to | ((uint32_t)from << 7);
+    if (from < N) return (uint32_t)(32 + to - N) | ((uint32_t)from << 7);
+    return (uint32_t)(64 + from - N) | ((uint32_t)to << 7);
 }
 
 // MINB: resident CTAs per SM the register budget is set for; PF: fetch the entry of the NEXT state right after a hop is
@@ -215,7 +306,6 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         const int slog = tlog + glog - 5;  // log2(table entries per run) >= 1
         const int hshift = 32 - slog;
         const uint32_t grp = (uint32_t)lane >> glog;
-        unsigned char *const tbase = wtab + ((size_t)grp << slog) * LENTB;
         const uint32_t gofs = (grp << slog) * LENTB;  // (byte offsets inside a warp slot's table fit 32 bits: <= 2^16 entries)
 #define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
         const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
@@ -286,19 +376,31 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                 }
             }
 
-            // ---- steps 2 and 3: warp-cooperative evaluation for the threads that missed (need) / fell into the rest of
-            //      the list (todo without need)
+            // ---- step 2: rest-of-list picks of threads that hit (from their entries, before this step writes any)
             uint32_t need = __ballot_sync(FULL, alive && !hit);
-            uint32_t todo = need | __ballot_sync(FULL, slow);
+            uint32_t slowm = __ballot_sync(FULL, slow);
             bool died = false;
-            if (todo) __syncwarp();  // (step 1's reads of the table are ordered before step 2's writes)
-            while (todo) {
-                const int t = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const bool build = (need >> t) & 1u;
+            if (need | slowm) __syncwarp();  // (step 1's reads of the table are ordered before this step's writes)
+            while (slowm) {
+                const int t = __ffs(slowm) - 1;
+                slowm &= slowm - 1;
+                const uint32_t occu = __shfl_sync(FULL, occ, t);
+                const unsigned char *ent = wtab + (size_t)(__shfl_sync(FULL, gofs, t) + ((occu * 0x9E3779B1u) >> hshift) * LENTB);
+                const float rest_tot = ldg_f32(ent + 256 + lane * 4);
+                const float e_me = ldg_f32(ent + 384 + lane * 4);
+                const uint32_t code_l = ldg_u16(ent + 16 + (lane >> 3) * 64 + (lane & 7) * 2);
+                const double total = ldg_f64(ent + 64), mtop = ldg_f64(ent + 72);
+                const float ve_mine = (lane < P) ? lds_f(a_ve + (uint32_t)(t * PV + lane) * 4u) : 0.0f;
+                const uint32_t rcode = slow_pick(occu, accm, __shfl_sync(FULL, nb, t), __shfl_sync(FULL, xr, t), total, mtop, rest_tot, e_me,
+                                                 ve_mine, code_l, lane, N, P, a_col_me, a_elF_e, a_elR_e);
+                if (lane == t) code = rcode;
+            }
+
+            // ---- step 3: warp-cooperative evaluation of the states that are not in the table
+            while (need) {
+                const int t = __ffs(need) - 1;
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 const float nbt = __shfl_sync(FULL, nb, t);
-                const uint32_t xt = __shfl_sync(FULL, xr, t);
                 const double E64 = (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u);
                 float ve_mine = 0.0f;  // electrode `lane` of trajectory t
                 __syncwarp();
@@ -326,149 +428,72 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     if (sl_r >= NR) sv = 0.0f;
                 }
                 if (lane == 31) sv = 0.0f;
-                double total = (double)sv + (double)rest_tot;
+                double mtop = (double)sv, total = (double)rest_tot;  // mass of the slot events | of everything
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+                for (int d = 16; d > 0; d >>= 1) {
+                    mtop += __shfl_xor_sync(FULL, mtop, d);
+                    total += __shfl_xor_sync(FULL, total, d);
+                }
+                total += mtop;
+                // threads of this run that wait on this very state (t among them) are all served by this evaluation
+                const uint32_t grp_t = __shfl_sync(FULL, grp, t);
+                uint32_t same = __ballot_sync(FULL, ((need >> lane) & 1u) && occ == occu && grp == grp_t);
+                need &= ~same;
                 if (!(total > 0.0)) {  // no transition possible (simulation.go:297 would divide by zero)
-                    if (lane == t) { alive = false; dead = true; }
+                    if ((same >> lane) & 1u) { alive = false; dead = true; }
                     died = true;
                     continue;
                 }
                 const bool occ_a = (occu >> sl_a) & 1u;
+                // slot code: event | acceptor << 7 | (rate > 0) << 12
                 const uint32_t mycode = (((uint32_t)spn < (uint32_t)N) ? (uint32_t)spn : ((uint32_t)spn - (uint32_t)N + (occ_a ? 32u : 64u))) |
-                                        ((uint32_t)sl_a << 7);
-                bool t_slow = !build;
-                if (build) {
-                    const double inv = 1.0 / total;
-                    const float rtot = (float)inv;
-                    // slots by decreasing rate: bitonic network on (rate bits with the 5 low mantissa bits replaced by
-                    // 31 - slot) -- unique keys; the order only decides which events share the first chunk, not the result
-                    uint32_t skey = (__float_as_uint(sv) & ~31u) | (uint32_t)(31 - lane);
+                                        ((uint32_t)sl_a << 7) | (sv > 0.0f ? 4096u : 0u);
+                const double inv = 1.0 / total;
+                const float rtot = (float)inv;
+                // slots by decreasing rate: bitonic network on (rate bits with the 5 low mantissa bits replaced by
+                // 31 - slot) -- unique keys; the order only decides which events share the first chunk, not the result
+                uint32_t skey = (__float_as_uint(sv) & ~31u) | (uint32_t)(31 - lane);
 #pragma unroll
-                    for (int kk = 2; kk <= 32; kk <<= 1) {
+                for (int kk = 2; kk <= 32; kk <<= 1) {
 #pragma unroll
-                        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                            const uint32_t other = __shfl_xor_sync(FULL, skey, jj);
-                            const bool keepmax = ((lane & jj) == 0) == ((lane & kk) == 0);
-                            skey = keepmax ? max(skey, other) : min(skey, other);
-                        }
-                    }
-                    const int ssrc = 31 - (int)(skey & 31u);
-                    const float ssv = __shfl_sync(FULL, sv, ssrc);
-                    const uint32_t scode = __shfl_sync(FULL, mycode, ssrc);
-                    const double incl = scan_d((double)ssv);
-                    const uint32_t thr = __double2uint_rn(incl * inv * 4294967296.0);  // (saturates at 2^32 - 1)
-                    if (use_table) {
-                        const unsigned long long tb_t = __shfl_sync(FULL, (unsigned long long)tbase, t);
-                        const uint32_t tagy_t = __shfl_sync(FULL, tagy, t);
-                        unsigned char *ent = (unsigned char *)tb_t + (size_t)(((occu * 0x9E3779B1u) >> hshift) * LENTB);
-                        unsigned char *ch = ent + (uint32_t)(lane >> 3) * 64u;
-                        stg_u32(ch + 32 + (lane & 7) * 4, thr);
-                        stg_u16(ch + 16 + (lane & 7) * 2, scode);
-                        if (lane == 0) stg_u4(ent, make_uint4(occu, __float_as_uint(rtot), tagx, tagy_t));
-                        __syncwarp();
-                    }
-                    // every waiting thread of this run that sits in this very state is served from the registers
-                    const uint32_t grp_t = __shfl_sync(FULL, grp, t);
-                    uint32_t same = __ballot_sync(FULL, ((need >> lane) & 1u) && occ == occu && grp == grp_t);
-                    need &= ~same;
-                    while (same) {
-                        const int t2 = __ffs(same) - 1;
-                        same &= same - 1;
-                        const uint32_t x2 = __shfl_sync(FULL, xr, t2);
-                        const uint32_t b = __ballot_sync(FULL, x2 < thr);
-                        const uint32_t c2 = __shfl_sync(FULL, scode, b ? __ffs(b) - 1 : 0);
-                        if (lane == t2) rt = rtot;
-                        if (b) {
-                            if (lane == t2) code = c2;
-                            todo &= ~(1u << t2);
-                        } else if (t2 == t) t_slow = true;  // (others stay in todo, now without their need bit)
+                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                        const uint32_t other = __shfl_xor_sync(FULL, skey, jj);
+                        const bool keepmax = ((lane & jj) == 0) == ((lane & kk) == 0);
+                        skey = keepmax ? max(skey, other) : min(skey, other);
                     }
                 }
-                if (t_slow) {
-                    // ---- the rest of the list: exact two-level pick over all events EXCEPT the ones that own a slot
-                    int sk[NR];
-#pragma unroll
-                    for (int rr = 0; rr < NR; ++rr) sk[rr] = (rr < n_slots && tk[rr] > 0.0f) ? pk[rr] : -1;
-                    double mtop = (double)sv;  // mass of the slot events
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) mtop += __shfl_xor_sync(FULL, mtop, d);
-                    const double rres = ((double)xt + 0.5) * 2.3283064365386963e-10 * total - mtop;
-                    const double incl = scan_d((double)rest_tot);
-                    double ex = __shfl_up_sync(FULL, incl, 1);
-                    if (lane == 0) ex = 0.0;
-                    const uint32_t rpos = __ballot_sync(FULL, rest_tot > 0.0f);
-                    uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
-                    if (!b2) b2 = rpos & (0u - rpos);
-                    int istar = -1;
-                    float rf = BIGE;
-                    if (b2) {
-                        istar = 31 - __clz(b2);
-                        rf = __shfl_sync(FULL, (float)(rres - ex), istar);
+                const int ssrc = 31 - (int)(skey & 31u);
+                const float ssv = __shfl_sync(FULL, sv, ssrc);
+                const uint32_t scode = __shfl_sync(FULL, mycode, ssrc);
+                const double incl = scan_d((double)ssv);
+                const uint32_t thr = __double2uint_rn(incl * inv * 4294967296.0);  // (saturates at 2^32 - 1)
+                if (use_table) {
+                    const uint32_t tagy_t = __shfl_sync(FULL, tagy, t);
+                    unsigned char *ent = wtab + (size_t)(__shfl_sync(FULL, gofs, t) + ((occu * 0x9E3779B1u) >> hshift) * LENTB);
+                    unsigned char *ch = ent + (uint32_t)(lane >> 3) * 64u;
+                    stg_u32(ch + 32 + (lane & 7) * 4, thr);
+                    stg_u16(ch + 16 + (lane & 7) * 2, scode);
+                    stg_f32(ent + 256 + lane * 4, rest_tot);
+                    stg_f32(ent + 384 + lane * 4, e_me);
+                    if (lane == 0) {
+                        stg_f64(ent + 64, total);
+                        stg_f64(ent + 72, mtop);
+                        stg_u4(ent, make_uint4(occu, __float_as_uint(rtot), tagx, tagy_t));
                     }
-                    uint32_t rcode;
-                    if (istar < 0) {
-                        // no mass outside the slots (rounding): the last slot with a positive rate
-                        const uint32_t posu = __ballot_sync(FULL, sv > 0.0f);  // (total > 0: not empty)
-                        rcode = __shfl_sync(FULL, mycode, 31 - __clz(posu));
-                    } else {
-                        int from, to;
-                        int skip[NR];
-#pragma unroll
-                        for (int rr = 0; rr < NR; ++rr) skip[rr] = (int)bcast_u((uint32_t)(sk[rr] + 1), istar, lane) - 1;
-                        const int ptop = (int)bcast_u((uint32_t)pk[0], istar, lane);  // rounding fallback: the acceptor's largest event
-                        const bool rowocc = (occu >> istar) & 1u;
-                        const float e_star = lds_f(a_mir + istar * 4);
-                        bool keepA = true, keepE = true;  // target `lane` / electrode `lane` does not own a slot
-#pragma unroll
-                        for (int rr = 0; rr < NR; ++rr) {
-                            keepA = keepA && lane != skip[rr];
-                            keepE = keepE && N + lane != skip[rr];
-                        }
-                        if (rowocc) {
-                            from = istar;
-                            to = -1;
-                            int lastA = -1;
-                            float sA = 0.0f;
-                            const uint32_t emp = ~occu & accm;
-                            if (emp) {  // acceptor targets: istar -> empty `lane`
-                                float rr = 0.0f;
-                                if (((emp >> lane) & 1u) && keepA) {
-                                    const float2 v = lds_f2(a_col_me + istar * 8);
-                                    rr = ma(v.x, v.y, e_me, e_star, nbt);
-                                }
-                                const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
-                                if (nz) {
-                                    const float s = scan_f<5>(rr);
-                                    const uint32_t b3 = __ballot_sync(FULL, s >= rf) & nz;
-                                    if (b3) to = __ffs(b3) - 1;
-                                    else {
-                                        lastA = 31 - __clz(nz);
-                                        sA = __shfl_sync(FULL, s, 31);
-                                    }
-                                }
-                            }
-                            if (to < 0) {  // electrode targets: istar -> electrode `lane`
-                                float rr = 0.0f;
-                                if (lane < P && keepE)
-                                    rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nbt, 0.0f));
-                                const int e = pick_group<5>(rr, rf - sA);
-                                to = (e >= 0) ? N + e : lastA;
-                            }
-                            if (to < 0) to = ptop;
-                        } else {  // empty acceptor: events electrode `lane` -> istar
-                            to = istar;
-                            float rr = 0.0f;
-                            if (lane < P && keepE)
-                                rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nbt, 0.0f));
-                            from = pick_group<5>(rr, rf);
-                            from = (from >= 0) ? from + N : ptop;
-                        }
-                        if (from < N && to < N) rcode = (uint32_t)to | ((uint32_t)from << 7);
-                        else if (from < N) rcode = (uint32_t)(32 + to - N) | ((uint32_t)from << 7);
-                        else rcode = (uint32_t)(64 + from - N) | ((uint32_t)to << 7);
+                    __syncwarp();
+                }
+                while (same) {
+                    const int t2 = __ffs(same) - 1;
+                    same &= same - 1;
+                    const uint32_t x2 = __shfl_sync(FULL, xr, t2);
+                    const uint32_t bb = __ballot_sync(FULL, x2 < thr);
+                    uint32_t c2;
+                    if (bb) c2 = __shfl_sync(FULL, scode, __ffs(bb) - 1);
+                    else c2 = slow_pick(occu, accm, nbt, x2, total, mtop, rest_tot, e_me, ve_mine, mycode, lane, N, P, a_col_me, a_elF_e, a_elR_e);
+                    if (lane == t2) {
+                        code = c2;
+                        rt = rtot;
                     }
-                    if (lane == t) code = rcode;
                 }
             }
             if (died && !__any_sync(FULL, alive)) {
@@ -567,7 +592,7 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
 }
 
 // plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the table
-// E.gtab = warp_slots * 2^E.gtab_log * 256 bytes from it.
+// E.gtab = warp_slots * 2^E.gtab_log * 512 bytes from it.
 cudaError_t launch_lanes(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan) {
     if (E.B <= 0) {
         if (plan) plan->warp_slots = 0;

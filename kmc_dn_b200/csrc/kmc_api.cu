@@ -50,7 +50,7 @@ struct kmcb200_layout {
     void *gtab = nullptr;
     size_t gtab_bytes = 0;
     uint32_t launch_id = 0;  // tag of the second-level entries (kmc_internal.cuh)
-    // state table of the thread-per-trajectory kernel (hop_lanes.cu: warp_slots x 2^tlog x 256 B), grow-only
+    // state table of the thread-per-trajectory kernel (hop_lanes.cu: warp_slots x 2^tlog x 512 B), grow-only
     void *ltab = nullptr;
     size_t ltab_bytes = 0;
     uint32_t lanes_launch_id = 0;
@@ -339,14 +339,14 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             E.gtab = nullptr; E.gtab_log = 6;
             if (!(E.lanes_flags & 1)) {
                 // table entries per warp slot (shared by the warp's runs of identical members: a run of g gets g/32 of them)
-                int tlog = th < 3000 ? 12 : 14;
+                int tlog = th < 3000 ? 11 : 13;
                 if (const char *ev = getenv("KMCB200_LTAB_LOG")) tlog = atoi(ev);
                 if (tlog < 6) tlog = 6;
                 if (tlog > 16) tlog = 16;
                 MemoPlan plan{0};
                 le = launch_lanes(D, E, st, nullptr, &plan);
                 if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-                size_t bytes = ((size_t)plan.warp_slots << tlog) * 256;
+                size_t bytes = ((size_t)plan.warp_slots << tlog) * 512;
                 if (bytes > lay->ltab_bytes) {
                     if (lay->ltab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ltab)); lay->ltab = nullptr; lay->ltab_bytes = 0; }
                     while (tlog >= 6 && cudaMalloc(&lay->ltab, bytes) != cudaSuccess) {  // a cache: halve it until it fits
