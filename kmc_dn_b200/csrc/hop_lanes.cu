@@ -84,6 +84,18 @@ __device__ __forceinline__ void ldg_head(const unsigned char *p, uint4 &h, uint4
         : "l"(p)
         : "memory");
 }
+// the same with four 128-bit loads (these allocate in L1; the 256-bit ones are served from L2)
+__device__ __forceinline__ void ldg_head128(const unsigned char *p, uint4 &h, uint4 &c, uint4 &a, uint4 &b) {
+    asm volatile(
+        "ld.global.v4.u32 {%0, %1, %2, %3}, [%16];\n\t"
+        "ld.global.v4.u32 {%4, %5, %6, %7}, [%16+16];\n\t"
+        "ld.global.v4.u32 {%8, %9, %10, %11}, [%16+32];\n\t"
+        "ld.global.v4.u32 {%12, %13, %14, %15}, [%16+48];"
+        : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w),
+          "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+        : "l"(p)
+        : "memory");
+}
 // codes + thresholds of a later chunk (48 B at p = entry + 64 c + 16)
 __device__ __forceinline__ void ldg_chunk(const unsigned char *p, uint4 &c, uint4 &a, uint4 &b) {
     asm volatile(
@@ -194,9 +206,10 @@ __device__ __noinline__ uint32_t slow_pick(uint32_t occu, uint32_t accm, float n
     return (uint32_t)(64 + from - N) | ((uint32_t)to << 7);
 }
 
-// MINB: resident CTAs per SM the register budget is set for; PF: fetch the entry of the NEXT state right after a hop is
-// applied (the loads fly while the next hop's variates are generated)
-template <int PT, bool DBG, int NR, int MINB, bool PF>
+// MINB: resident CTAs per SM the register budget is set for; W256: read the first chunk with two 256-bit loads (served
+// from L2) instead of four 128-bit ones (which allocate in L1).  The entry of the NEXT state is fetched right after a
+// hop is applied: the loads fly while the next hop's variates are generated.
+template <int PT, bool DBG, int NR, int MINB, bool W256>
 __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = LanesGeom<PT>;
     constexpr int PV = G::PV;
@@ -307,6 +320,11 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         const int hshift = 32 - slog;
         const uint32_t grp = (uint32_t)lane >> glog;
         const uint32_t gofs = (grp << slog) * LENTB;  // (byte offsets inside a warp slot's table fit 32 bits: <= 2^16 entries)
+#define LANES_HEAD(p_)                                  \
+    do {                                                \
+        if (W256) ldg_head(p_, hd, tc, ta, tb);         \
+        else ldg_head128(p_, hd, tc, ta, tb);           \
+    } while (0)
 #define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
         const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
 
@@ -317,7 +335,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         long long n_miss = 0;
         uint4 r = make_uint4(0u, 0u, 0u, 0u);
         uint4 hd = make_uint4(0u, 0u, 0u, 0u), ta = hd, tb = hd, tc = hd;  // (launch ids start at 1: never a valid header)
-        if (PF && alive && use_table) ldg_head(LANES_ENT(occ), hd, tc, ta, tb);
+        if (alive && use_table) LANES_HEAD(LANES_ENT(occ));
 
         // segments: a segment never straddles a 64-hop variate block or the prehops boundary
         bool stop = false;
@@ -353,7 +371,6 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
             uint32_t code = 0;
             float rt = 0.0f;
             bool hit = false, slow = false;
-            if (!PF && alive && use_table) ldg_head(LANES_ENT(occ), hd, tc, ta, tb);
             // (thresholds never decrease: the last clause is always true for a valid entry -- it keeps ptxas from
             //  sinking the threshold loads below the branch, which would cost a second round trip)
             hit = alive && use_table && hd.x == occ && hd.z == tagx && hd.w == tagy && tb.w >= ta.x;
@@ -520,7 +537,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
                     tp[0] = from;
                     tp[1] = to;
                 }
-                if (PF && use_table) ldg_head(LANES_ENT(occ), hd, tc, ta, tb);
+                if (use_table) LANES_HEAD(LANES_ENT(occ));
             }
             }  // hops of the segment
             h0 = hend;
@@ -551,7 +568,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
     }  // blocks of members
 }
 
-template <int PT, int MINB, bool PF>
+template <int PT, int MINB, bool W256>
 static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     using G = LanesGeom<PT>;
     const bool dbg = E.trace || E.misses;
@@ -559,9 +576,9 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
     // (the variants exist for the production instantiation only; the tracing one uses the defaults)
-    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 6, true> : kmc_lanes_kernel<PT, false, 3, MINB, PF>)
-              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 6, true> : kmc_lanes_kernel<PT, false, 2, MINB, PF>)
-                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 6, true> : kmc_lanes_kernel<PT, false, 1, MINB, PF>);
+    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 6, true> : kmc_lanes_kernel<PT, false, 3, MINB, W256>)
+              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 6, true> : kmc_lanes_kernel<PT, false, 2, MINB, W256>)
+                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 6, true> : kmc_lanes_kernel<PT, false, 1, MINB, W256>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 0, per_sm = 0;
@@ -583,7 +600,7 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
 
 template <int PT>
 static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
-    // experiment knobs (profiles/run_lanes.py): KMCB200_LANES_MINB = 5 | 6, KMCB200_LANES_PF = 0 | 1
+    // experiment knobs (profiles/run_lanes.py): KMCB200_LANES_MINB = 5 | 6, KMCB200_LANES_PF = 0 (128-bit loads) | 1 (256-bit)
     int minb = LANES_MIN_CTAS, pf = 1;
     if (const char *ev = getenv("KMCB200_LANES_MINB")) minb = atoi(ev);
     if (const char *ev = getenv("KMCB200_LANES_PF")) pf = atoi(ev);

@@ -194,7 +194,7 @@ size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 }  // namespace
 
 // MODE_FAST, N <= 31: ensembles of at least this many members run on the thread-per-trajectory kernel (hop_lanes.cu)
-static const int64_t kLanesAutoMinB = 32768;
+static const int64_t kLanesAutoMinB = 65536;
 
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");

@@ -260,19 +260,19 @@ def test_kernel_selection(golden_py):
     from kmc_dn_b200.ensemble import last_kernel
     c = golden_py["fx_rnd_min_max_0"]
     lay = _layout(c)
-    for B, want in ((40000, "kmc_lanes_kernel"), (100, "kmc_memo_kernel")):
+    for B, want in ((70000, "kmc_lanes_kernel"), (100, "kmc_memo_kernel")):
         r = lay.run(50, c["kT"], np.tile(c["electrode_v"], (B, 1)), E_constant=np.tile(c["E_constant"], (B, 1)), seed=1)
         assert last_kernel() == want, (B, last_kernel())
         assert np.isfinite(r["time"]).all()
-    lay.run(50, c["kT"], np.tile(c["electrode_v"], (40000, 1)), E_constant=np.tile(c["E_constant"], (40000, 1)), seed=1,
+    lay.run(50, c["kT"], np.tile(c["electrode_v"], (70000, 1)), E_constant=np.tile(c["E_constant"], (70000, 1)), seed=1,
             kernel="warp")
     assert last_kernel() == "kmc_memo_kernel"
-    lay.run(50, c["kT"], np.tile(c["electrode_v"], (40000, 1)), E_constant=np.tile(c["E_constant"], (40000, 1)), seed=1,
+    lay.run(50, c["kT"], np.tile(c["electrode_v"], (70000, 1)), E_constant=np.tile(c["E_constant"], (70000, 1)), seed=1,
             record=True)  # record outputs exist only in the warp-per-trajectory kernel
     assert last_kernel() == "kmc_memo_kernel"
     lay.close()
     d = synthetic_layout(40, 4, 3)
     lay = _layout(d)
-    lay.run(20, d["kT"], np.tile(d["electrode_v"], (40000, 1)), E_constant=np.tile(d["E_constant"], (40000, 1)), seed=1)
+    lay.run(20, d["kT"], np.tile(d["electrode_v"], (70000, 1)), E_constant=np.tile(d["E_constant"], (70000, 1)), seed=1)
     assert last_kernel() == "kmc_wide_kernel"
     lay.close()
