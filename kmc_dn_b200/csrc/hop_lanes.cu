@@ -48,8 +48,6 @@
 //
 // RNG: the same Philox4x32-10 numbering as hop_memo.cu (key = seed, counter = (64-hop block * 32 + pair, global member
 // index), two hops per call), so streams do not depend on batching, on the number of GPUs or on the kernel's geometry.
-#include <cstdlib>
-
 #include "memo_common.cuh"
 
 namespace kmcb200 {
@@ -79,18 +77,6 @@ __device__ __forceinline__ void ldg_head(const unsigned char *p, uint4 &h, uint4
     asm volatile(
         "ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
         "ld.global.v8.u32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%16+32];"
-        : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w),
-          "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-        : "l"(p)
-        : "memory");
-}
-// the same with four 128-bit loads (these allocate in L1; the 256-bit ones are served from L2)
-__device__ __forceinline__ void ldg_head128(const unsigned char *p, uint4 &h, uint4 &c, uint4 &a, uint4 &b) {
-    asm volatile(
-        "ld.global.v4.u32 {%0, %1, %2, %3}, [%16];\n\t"
-        "ld.global.v4.u32 {%4, %5, %6, %7}, [%16+16];\n\t"
-        "ld.global.v4.u32 {%8, %9, %10, %11}, [%16+32];\n\t"
-        "ld.global.v4.u32 {%12, %13, %14, %15}, [%16+48];"
         : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w),
           "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
         : "l"(p)
@@ -206,11 +192,11 @@ __device__ __noinline__ uint32_t slow_pick(uint32_t occu, uint32_t accm, float n
     return (uint32_t)(64 + from - N) | ((uint32_t)to << 7);
 }
 
-// MINB: resident CTAs per SM the register budget is set for; W256: read the first chunk with two 256-bit loads (served
-// from L2) instead of four 128-bit ones (which allocate in L1).  The entry of the NEXT state is fetched right after a
-// hop is applied: the loads fly while the next hop's variates are generated.
-template <int PT, bool DBG, int NR, int MINB, bool W256>
-__global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L, const EnsembleDev E) {
+// The entry of the NEXT state is fetched right after a hop is applied: the loads fly while the next hop's variates are
+// generated.  (Measured on C3: 6 resident CTAs per SM beat 5, 7 and 8; two 256-bit loads -- served from L2 -- beat four
+// 128-bit loads that allocate in L1, 6.3e10 against 5.7e10 hops/s.)
+template <int PT, bool DBG, int NR>
+__global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = LanesGeom<PT>;
     constexpr int PV = G::PV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -320,11 +306,7 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
         const int hshift = 32 - slog;
         const uint32_t grp = (uint32_t)lane >> glog;
         const uint32_t gofs = (grp << slog) * LENTB;  // (byte offsets inside a warp slot's table fit 32 bits: <= 2^16 entries)
-#define LANES_HEAD(p_)                                  \
-    do {                                                \
-        if (W256) ldg_head(p_, hd, tc, ta, tb);         \
-        else ldg_head128(p_, hd, tc, ta, tb);           \
-    } while (0)
+#define LANES_HEAD(p_) ldg_head(p_, hd, tc, ta, tb)
 #define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
         const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
 
@@ -568,19 +550,20 @@ __global__ void __launch_bounds__(128, MINB) kmc_lanes_kernel(const LayoutDev L,
     }  // blocks of members
 }
 
-template <int PT, int MINB, bool W256>
-static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
+template <int PT>
+static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     using G = LanesGeom<PT>;
     const bool dbg = E.trace || E.misses;
     const int warps = 4;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
+    // ranked events per acceptor: as many as the 31 slots hold (3 for N <= 10, 2 up to N = 24, else 1)
     const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
-    // (the variants exist for the production instantiation only; the tracing one uses the defaults)
-    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3, 6, true> : kmc_lanes_kernel<PT, false, 3, MINB, W256>)
-              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2, 6, true> : kmc_lanes_kernel<PT, false, 2, MINB, W256>)
-                        : (dbg ? kmc_lanes_kernel<PT, true, 1, 6, true> : kmc_lanes_kernel<PT, false, 1, MINB, W256>);
+    auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3> : kmc_lanes_kernel<PT, false, 3>)
+              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2> : kmc_lanes_kernel<PT, false, 2>)
+                        : (dbg ? kmc_lanes_kernel<PT, true, 1> : kmc_lanes_kernel<PT, false, 1>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
+    // persistent CTAs: as many as stay resident; every warp loops over blocks of 32 members
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -596,16 +579,6 @@ static cudaError_t launch_lanes_v(const LayoutDev &L, const EnsembleDev &E, cuda
     kern<<<grid, warps * 32, smem, st>>>(L, E);
     if (launches) ++*launches;
     return cudaGetLastError();
-}
-
-template <int PT>
-static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
-    // experiment knobs (profiles/run_lanes.py): KMCB200_LANES_MINB = 5 | 6, KMCB200_LANES_PF = 0 (128-bit loads) | 1 (256-bit)
-    int minb = LANES_MIN_CTAS, pf = 1;
-    if (const char *ev = getenv("KMCB200_LANES_MINB")) minb = atoi(ev);
-    if (const char *ev = getenv("KMCB200_LANES_PF")) pf = atoi(ev);
-    if (minb >= 6) return pf ? launch_lanes_v<PT, 6, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 6, false>(L, E, st, launches, plan_only);
-    return pf ? launch_lanes_v<PT, 5, true>(L, E, st, launches, plan_only) : launch_lanes_v<PT, 5, false>(L, E, st, launches, plan_only);
 }
 
 // plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the table

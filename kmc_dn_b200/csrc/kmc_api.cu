@@ -339,7 +339,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             E.gtab = nullptr; E.gtab_log = 6;
             if (!(E.lanes_flags & 1)) {
                 // table entries per warp slot (shared by the warp's runs of identical members: a run of g gets g/32 of them)
-                int tlog = th < 3000 ? 11 : 13;
+                int tlog = th < 3000 ? 11 : (th < 10000 ? 13 : 14);
                 if (const char *ev = getenv("KMCB200_LTAB_LOG")) tlog = atoi(ev);
                 if (tlog < 6) tlog = 6;
                 if (tlog > 16) tlog = 16;

@@ -54,7 +54,6 @@ def main():
     ap.add_argument("--c4", action="store_true")
     ap.add_argument("--crossover", default="", help="member counts at which both kernels are timed, e.g. 8192,16384,32768")
     ap.add_argument("--kernels", default="warp,lanes")
-    ap.add_argument("--variants", default="", help="lanes kernel experiment knobs, e.g. 5:0,5:1,6:1 (min CTAs per SM : prefetch)")
     args = ap.parse_args()
     from kmc_dn_b200 import workloads
     from kmc_dn_b200.ensemble import Layout
@@ -63,18 +62,13 @@ def main():
     lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R)
     for k in args.kernels.split(","):
         tl = [None] + ([int(x) for x in args.tlogs.split(",")] if (k == "lanes" and args.tlogs) else [])
-        vl = [None] + ([v for v in args.variants.split(",")] if (k == "lanes" and args.variants) else [])
-        for v in vl:
-            if v is not None:
-                os.environ["KMCB200_LANES_MINB"], os.environ["KMCB200_LANES_PF"] = v.split(":")
-            for t in tl:
-                if t is not None:
-                    os.environ["KMCB200_LTAB_LOG"] = str(t)
-                r = measure(lay, lt, w, args.hops, 0, k)
-                r["workload"] = "c3"; r["ltab_log"] = t; r["variant"] = v
-                print(json.dumps(r), flush=True)
-            os.environ.pop("KMCB200_LTAB_LOG", None)
-        os.environ.pop("KMCB200_LANES_MINB", None); os.environ.pop("KMCB200_LANES_PF", None)
+        for t in tl:
+            if t is not None:
+                os.environ["KMCB200_LTAB_LOG"] = str(t)
+            r = measure(lay, lt, w, args.hops, 0, k)
+            r["workload"] = "c3"; r["ltab_log"] = t
+            print(json.dumps(r), flush=True)
+        os.environ.pop("KMCB200_LTAB_LOG", None)
     for b in [int(x) for x in args.crossover.split(",") if x]:
         wb = workloads.c3_voltage_search(n_controls=max(1, b // (4 * args.seeds)), seeds=args.seeds)
         for k in ("warp", "lanes"):

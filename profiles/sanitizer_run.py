@@ -5,7 +5,9 @@
     compute-sanitizer --tool racecheck python profiles/sanitizer_run.py
 
 Covers hop_memo.cu (1 / 2 / 3 ranked events per acceptor, cache on / off, record + trace instantiation, second-level
-table) and hop_wide.cu (1 / 2 / 4 / 8 acceptors per lane, shared-memory and cp.async-ring sweeps, cache on / off)."""
+table), hop_wide.cu (1 / 2 / 4 / 8 acceptors per lane, shared-memory and cp.async-ring sweeps, cache on / off) and
+hop_lanes.cu (thread per trajectory: 1 / 2 / 3 ranked events, table on / off, runs of identical members, ragged
+ensembles, trace instantiation).  `--lanes-only` restricts the run to the last one."""
 import os
 import sys
 
@@ -17,7 +19,28 @@ from kmc_dn_b200.ensemble import Layout  # noqa: E402
 from tests.util import synthetic_layout  # noqa: E402
 
 
+def lanes():
+    for N, P in [(5, 3), (10, 2), (16, 8), (30, 8), (31, 1), (25, 0)]:
+        c = synthetic_layout(N, P, 11 + N, fill=0.6)
+        lay = Layout(c["N"], c["P"], c["distances"], c["transitions_constant"], nu=c["nu"], I_0=c["I_0"], R=c["R"])
+        B, hops = 77, 250  # three warps, the last one ragged; runs of 4 identical members
+        V = np.tile(c["electrode_v"], (B, 1)) + (np.arange(B) // 4)[:, None]
+        E = np.tile(c["E_constant"], (B, 1))
+        kw = dict(E_constant=E, occupation0=c["occupation"], seed=3, kernel="lanes", want_occupation=True)
+        a = lay.run(hops, c["kT"], V, memo=True, **kw)
+        b = lay.run(hops, c["kT"], V, memo=False, **kw)
+        assert np.array_equal(a["time"], b["time"]) and np.array_equal(a["electrode_occupation"], b["electrode_occupation"])
+        r = lay.run(hops, c["kT"], V[:40], E_constant=E[:40], occupation0=c["occupation"], seed=4, prehops=50, trace=True,
+                    want_occupation=True, want_site_energies=True, want_misses=True, kernel="lanes")
+        assert np.isfinite(r["time"]).any()
+        lay.close()
+        print(f"lanes N={N} P={P}: ok", flush=True)
+
+
 def main():
+    lanes()
+    if "--lanes-only" in sys.argv:
+        return
     cases = [(5, 3), (10, 2), (16, 8), (30, 8), (31, 1), (32, 8), (48, 8), (100, 5), (256, 8)]
     for N, P in cases:
         c = synthetic_layout(N, P, 11 + N, fill=0.85)
