@@ -391,7 +391,7 @@ def roofline(hops_per_s_gpu, ms_per_step, B, hops, lt, stats, lay, device, kerne
             "traffic_note": "dram__bytes_read+write of the ncu capture, scaled per member to this launch.  Algorithmic "
                             f"bytes per member = {bytes_per_member} (inputs {8 * lt.P + 8 + lt.N} B, outputs {8 + 8 * lt.P} B); the rest "
                             "is the state table / second-level state cache (a few hundred 256-288 B entries per run of "
-                            "trajectories, > L2 in total) spilling to HBM -- working set by design, ~2 % of the HBM bandwidth",
+                            "trajectories, > L2 in total) spilling to HBM -- working set by design, 2-4 % of the HBM bandwidth",
             "sample": stats}
 
 
