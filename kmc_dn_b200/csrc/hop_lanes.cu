@@ -12,21 +12,23 @@
 //
 // hop_memo.cu (read its header first) runs one trajectory per WARP: a hop that finds its state in the cache still
 // costs 27 warp-instructions.  Here a warp carries 32 trajectories in lock-step, one per thread, and a hop whose
-// state is in the table is plain per-thread code: Philox, one hash, one 48-byte read of the entry's first chunk
-// (header + the 8 most likely events), a branch-free count of thresholds, the mask update -- about 3 warp-instructions
-// per hop and trajectory.  Only what is NOT in the table is warp-cooperative: the warp stops, evaluates the missing
-// state of one of its trajectories with the sweep of hop_memo.cu (lane i = acceptor i), parks the result and goes on.
+// state is in the table is plain per-thread code: Philox, one hash, one 64-byte read of the entry's first chunk
+// (header + the 8 most likely events), a branch-free count of thresholds, the mask update -- about 5.5 warp-
+// instructions per hop and trajectory.  Only what is NOT in the table is warp-cooperative: the warp stops, evaluates
+// the missing state of one of its trajectories with the sweep of hop_memo.cu (lane i = acceptor i), parks the result
+// and goes on.  Measured on C3 (1 M members x 1e4 hops, one B200): 6.5e10 hops/s against 2.1e10 of hop_memo.cu;
+// 8.5 warp-instructions per hop against 42.8 (profiles/ncu_r01_v8_lanes_kernel_final.txt).
 //
 // Table.  The cumulative rate structure is a PURE function of (layout, E_constant, electrode energies, kT, occupation
 // mask) -- the fp64 energies are exact sums of fp32 terms (hop_memo.cu) -- so trajectories with identical parameters
 // (the seeds of one voltage vector / temperature) SHARE one table: the warp detects aligned runs of 2..32 identical
-// members among its 32 and gives every run one direct-mapped table in global memory (hot entries live in L1 / L2; the
-// hardware caches replace the hand-managed first level of hop_memo.cu).  An entry (256 B) is keyed by the full
-// occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset (512 B):
+// members among its 32 and gives every run one direct-mapped table in global memory (hot entries live in L2; the
+// hardware cache replaces the hand-managed first level of hop_memo.cu).  An entry (512 B) is keyed by the full
+// occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset:
 //
 //     0   u32 key | f32 1/total | u32 launch id | u32 first member of the run + 1
 //     16 + 64c   8 x u16   codes of events 8c .. 8c+7: event (partner acceptor j | 32+e hole into electrode e | 64+e
-//                          hole out of electrode e) | acceptor << 7
+//                          hole out of electrode e) | acceptor << 7 | (rate > 0) << 12
 //     32 + 64c   8 x u32   their thresholds: inclusive cumulative rate / total in 0.32 fixed point   (c = 0 .. 3)
 //     64  f64 total rate | f64 mass of the slot events
 //     256 32 x f32  per acceptor: mass of its events outside the slots     384 32 x f32  per acceptor: site energy
@@ -34,17 +36,19 @@
 //    the rest-of-list picks, so that they need no second evaluation of the state)
 //
 // The events are the 31 event slots of hop_memo.cu (every acceptor's largest rates), SORTED by decreasing rate: on C3
-// the first chunk answers most hops with one 48-byte read.  The pick compares the raw 32-bit Philox output x against
-// the thresholds (event k iff thr[k-1] <= x < thr[k]) -- the same partition of [0,1) that hop_memo.cu's fp64 compare
-// against (x+0.5)/2^32 realises, in integers.  x >= thr[31] (the mass of all slot events; 0.2 % of the hops on C3)
-// takes the exact two-level pick over the rest of the list, warp-cooperatively, as in hop_memo.cu.
+// the first chunk answers most hops.  The pick compares the raw 32-bit Philox output x against the thresholds (event k
+// iff thr[k-1] <= x < thr[k]) -- the same partition of [0,1) that hop_memo.cu's fp64 compare against (x+0.5)/2^32
+// realises, in integers.  x >= thr[31] (the mass of all slot events: 0.4 % of the hops on C3 on average, up to 8 % for
+// some voltage vectors) takes the exact two-level pick over the rest of the list (slow_pick below), warp-cooperatively,
+// from the entry's second half.
 //
 // Lock-step and misses.  All 32 trajectories of a warp execute hop h together.  Step 1: every thread probes its
-// table; threads that hit resolve their event on their own.  Step 2: for every thread that missed, the warp evaluates
-// the state, writes the entry and resolves that thread's event from the registers right away (an entry may be evicted
-// by the next evaluation of the same step; nobody depends on re-reading it); threads of the same run that wait on the
-// SAME state are served by the same evaluation.  Step 3: rest-of-list picks.  Step 4: every thread applies its event.
-// With the table disabled (lanes_flags & 1) every hop takes step 2 -- same arithmetic, bit-identical results (tested).
+// table (the entry was fetched right after the previous hop); threads that hit resolve their event on their own.
+// Step 2: rest-of-list picks of threads that hit -- they READ entries, so they run before this step writes any.
+// Step 3: for every thread that missed, the warp evaluates the state, writes the entry and resolves from the registers
+// every waiting thread of the run that sits in this very state (an entry may be evicted by the next evaluation of the
+// same step; nobody depends on re-reading it).  Step 4: every thread applies its event.
+// With the table disabled (lanes_flags & 1) every hop takes step 3 -- same arithmetic, bit-identical results (tested).
 //
 // RNG: the same Philox4x32-10 numbering as hop_memo.cu (key = seed, counter = (64-hop block * 32 + pair, global member
 // index), two hops per call), so streams do not depend on batching, on the number of GPUs or on the kernel's geometry.
