@@ -10,4 +10,4 @@ mkdir -p gpurun_out
 (timeout 300 compute-sanitizer --tool memcheck python profiles/sanitizer_run.py --lanes-only) > gpurun_out/sanitizer_memcheck_lanes_r01.log 2>&1
 (timeout 300 compute-sanitizer --tool racecheck python profiles/sanitizer_run.py --lanes-only) > gpurun_out/sanitizer_racecheck_lanes_r01.log 2>&1
 (timeout 400 python profiles/run_lanes.py --c4 --crossover 65536,131072,262144) > gpurun_out/lanes.jsonl 2> gpurun_out/lanes.err
-tail -4 gpurun_out/final_tests.log; tail -2 gpurun_out/final_smoke.log; cut -c1-400 gpurun_out/bench_n1.jsonl; cut -c1-400 gpurun_out/bench_n1_reference.jsonl; tail -2 gpurun_out/sanitizer_memcheck_lanes_r01.log gpurun_out/sanitizer_racecheck_lanes_r01.log
+tail -4 gpurun_out/final_tests.log; tail -2 gpurun_out/final_smoke.log; cut -c1-400 gpurun_out/bench_n1.jsonl; cut -c1-400 gpurun_out/bench_n1_reference.jsonl; tail -n 2 gpurun_out/sanitizer_memcheck_lanes_r01.log; tail -n 2 gpurun_out/sanitizer_racecheck_lanes_r01.log
