@@ -1,9 +1,13 @@
 """CPU suite, part 2: electrostatics front end and the kmc_dn host class set-up against the reference's
 stored fixture fields (inputs pinned to fp64 round-off), plus the benchmark workload builders."""
+import os
+
 import numpy as np
 import pytest
 
 from tests.util import load_cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -185,3 +189,24 @@ def test_bench_refuses_to_run_without_gpu():
                          text=True, timeout=300)
     assert out.returncode != 0
     assert not [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_kernel_choice_argument():
+    """`kernel=` of Layout.run maps onto the C ABI's KMCB200_FLAG_LANES / _NO_LANES; unknown names are refused."""
+    from kmc_dn_b200 import _lib
+    from kmc_dn_b200.ensemble import _kernel_flags
+    assert _kernel_flags(None) == 0 and _kernel_flags("auto") == 0
+    assert _kernel_flags("lanes") == _lib.FLAG_LANES == 4 and _kernel_flags("warp") == _lib.FLAG_NO_LANES == 8
+    with pytest.raises(KeyError):
+        _kernel_flags("fastest")
+    header = open(os.path.join(ROOT, "include", "kmc_b200.h")).read()
+    assert "KMCB200_FLAG_LANES = 4" in header and "KMCB200_FLAG_NO_LANES = 8" in header
+
+
+def test_committed_ncu_summaries_feed_the_bench_roofline():
+    """bench.py's roofline reads warp-instructions per hop of the kernel that ran from profiles/ncu_r01_<kernel>_kernel.json."""
+    import json
+    for kernel in ("lanes", "memo", "wide"):
+        j = json.load(open(os.path.join(ROOT, "profiles", f"ncu_r01_{kernel}_kernel.json")))
+        assert j["warp_inst_per_hop"] > 1 and kernel in j["kernel"], kernel
+        assert 0 < j["issue_active_pct"] <= 100
