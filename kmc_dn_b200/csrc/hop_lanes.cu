@@ -57,6 +57,9 @@
 namespace kmcb200 {
 
 #define LENTB 512u  // bytes per table entry
+#ifndef LANES_RUNS_BY_LEADER
+#define LANES_RUNS_BY_LEADER 0  // 1: experiment, see the run detection in the kernel
+#endif
 #ifndef LANES_MIN_CTAS
 #define LANES_MIN_CTAS 6  // resident CTAs of 4 warps per SM the register budget is set for
 #endif
@@ -300,6 +303,18 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             }
             sp &= spk;
         }
+#if LANES_RUNS_BY_LEADER
+        // (experiment, not built by default, unmeasured: runs of ANY length and alignment -- e.g. the reference's 5 repeats
+        //  per fixture -- share a table; every run of the warp gets the same power-of-two share of the warp slot's entries)
+        const uint32_t lead_mask = ~sp;  // bit l = member l starts a run (bit 0 always does)
+        const int leader = 31 - __clz(lead_mask & (0xffffffffu >> (31 - lane)));
+        const int nruns = __popc(lead_mask);
+        const int slog = tlog - (nruns > 1 ? 32 - __clz(nruns - 1) : 0);  // log2(table entries per run) >= 1
+        const int hshift = 32 - slog;
+        const uint32_t grp = (uint32_t)leader;
+        const uint32_t gofs = ((uint32_t)__popc(lead_mask & ((1u << leader) - 1u)) << slog) * LENTB;
+        const uint32_t tagy = (uint32_t)(base + leader) + 1u;
+#else
         int glog = 0;  // log2(run length): the largest aligned power of two such that every run is uniform
         if ((sp | 0x00000001u) == FULL) glog = 5;
         else if ((sp | 0x00010001u) == FULL) glog = 4;
@@ -310,9 +325,10 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         const int hshift = 32 - slog;
         const uint32_t grp = (uint32_t)lane >> glog;
         const uint32_t gofs = (grp << slog) * LENTB;  // (byte offsets inside a warp slot's table fit 32 bits: <= 2^16 entries)
+        const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
+#endif
 #define LANES_HEAD(p_) ldg_head(p_, hd, tc, ta, tb)
 #define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
-        const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
 
         const uint64_t gm = E.member_index0 + (uint64_t)mc;
         bool alive = active, dead = false;

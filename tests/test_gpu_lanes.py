@@ -45,19 +45,19 @@ def _check_trace(c, r, occupation0):
         np.testing.assert_array_equal(r["electrode_occupation"][m], eo)
 
 
-@pytest.mark.parametrize("runs", ["of16", "distinct", "identical", "of4_ragged"])
+@pytest.mark.parametrize("runs", ["of16", "distinct", "identical", "of4_ragged", "of5"])
 def test_lanes_table_is_transparent(golden_py, fixtures_subset, runs):
     """The table memoises a pure function of (parameters, occupation): with it disabled (memo=False: every hop of
     every trajectory is evaluated from scratch) trace, time, tallies, occupation and energies are bit-identical --
     for runs of 16 seeds per voltage vector (shared tables), all-distinct members (one table each), 32 identical
-    members, and a ragged ensemble with runs of 4."""
+    members, a ragged ensemble with runs of 4, and runs of 5 (not aligned: one table per trajectory)."""
     cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
              "c2_grid_N16_P8": golden_py["c2_grid_N16_P8"], "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"],
              "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"]),
              "N31_P5": synthetic_layout(31, 5, 7), "N25_P0": synthetic_layout(25, 0, 8, fill=0.5)}
     for name, c in cases.items():
-        B, hops, P = {"of16": 96, "distinct": 64, "identical": 64, "of4_ragged": 77}[runs], 3000, c["P"]
-        rep = {"of16": 16, "distinct": 1, "identical": B, "of4_ragged": 4}[runs]
+        B, hops, P = {"of16": 96, "distinct": 64, "identical": 64, "of4_ragged": 77, "of5": 80}[runs], 3000, c["P"]
+        rep = {"of16": 16, "distinct": 1, "identical": B, "of4_ragged": 4, "of5": 5}[runs]
         V = np.tile(c["electrode_v"], (B, 1)) + (np.arange(B) // rep)[:, None] * 0.37
         E = np.tile(c["E_constant"], (B, 1)) + (np.arange(B) // rep)[:, None] * 0.11
         kT = c["kT"] * (1.0 + 0.05 * ((np.arange(B) // rep) % 3))
