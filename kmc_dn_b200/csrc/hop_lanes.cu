@@ -21,7 +21,7 @@
 //
 // Table.  The cumulative rate structure is a PURE function of (layout, E_constant, electrode energies, kT, occupation
 // mask) -- the fp64 energies are exact sums of fp32 terms (hop_memo.cu) -- so trajectories with identical parameters
-// (the seeds of one voltage vector / temperature) SHARE one table: the warp detects aligned runs of 2..32 identical
+// (the seeds of one voltage vector / temperature) SHARE one table: the warp detects the runs of consecutive identical
 // members among its 32 and gives every run one direct-mapped table in global memory (hot entries live in L2; the
 // hardware cache replaces the hand-managed first level of hop_memo.cu).  An entry (512 B) is keyed by the full
 // occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset:
@@ -57,9 +57,6 @@
 namespace kmcb200 {
 
 #define LENTB 512u  // bytes per table entry
-#ifndef LANES_RUNS_BY_LEADER
-#define LANES_RUNS_BY_LEADER 0  // 1: experiment, see the run detection in the kernel
-#endif
 #ifndef LANES_MIN_CTAS
 #define LANES_MIN_CTAS 6  // resident CTAs of 4 warps per SM the register budget is set for
 #endif
@@ -303,30 +300,16 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             }
             sp &= spk;
         }
-#if LANES_RUNS_BY_LEADER
-        // (experiment, not built by default, unmeasured: runs of ANY length and alignment -- e.g. the reference's 5 repeats
-        //  per fixture -- share a table; every run of the warp gets the same power-of-two share of the warp slot's entries)
+        // runs of identical members (any length, any alignment): every run of the warp gets the same power-of-two share
+        // of the warp slot's table entries
         const uint32_t lead_mask = ~sp;  // bit l = member l starts a run (bit 0 always does)
         const int leader = 31 - __clz(lead_mask & (0xffffffffu >> (31 - lane)));
         const int nruns = __popc(lead_mask);
         const int slog = tlog - (nruns > 1 ? 32 - __clz(nruns - 1) : 0);  // log2(table entries per run) >= 1
         const int hshift = 32 - slog;
         const uint32_t grp = (uint32_t)leader;
-        const uint32_t gofs = ((uint32_t)__popc(lead_mask & ((1u << leader) - 1u)) << slog) * LENTB;
+        const uint32_t gofs = ((uint32_t)__popc(lead_mask & ((1u << leader) - 1u)) << slog) * LENTB;  // (< 2^25: 32 bits)
         const uint32_t tagy = (uint32_t)(base + leader) + 1u;
-#else
-        int glog = 0;  // log2(run length): the largest aligned power of two such that every run is uniform
-        if ((sp | 0x00000001u) == FULL) glog = 5;
-        else if ((sp | 0x00010001u) == FULL) glog = 4;
-        else if ((sp | 0x01010101u) == FULL) glog = 3;
-        else if ((sp | 0x11111111u) == FULL) glog = 2;
-        else if ((sp | 0x55555555u) == FULL) glog = 1;
-        const int slog = tlog + glog - 5;  // log2(table entries per run) >= 1
-        const int hshift = 32 - slog;
-        const uint32_t grp = (uint32_t)lane >> glog;
-        const uint32_t gofs = (grp << slog) * LENTB;  // (byte offsets inside a warp slot's table fit 32 bits: <= 2^16 entries)
-        const uint32_t tagy = (uint32_t)(base + ((int64_t)grp << glog)) + 1u;
-#endif
 #define LANES_HEAD(p_) ldg_head(p_, hd, tc, ta, tb)
 #define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
 

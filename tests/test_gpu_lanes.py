@@ -50,7 +50,7 @@ def test_lanes_table_is_transparent(golden_py, fixtures_subset, runs):
     """The table memoises a pure function of (parameters, occupation): with it disabled (memo=False: every hop of
     every trajectory is evaluated from scratch) trace, time, tallies, occupation and energies are bit-identical --
     for runs of 16 seeds per voltage vector (shared tables), all-distinct members (one table each), 32 identical
-    members, a ragged ensemble with runs of 4, and runs of 5 (not aligned: one table per trajectory)."""
+    members, a ragged ensemble with runs of 4, and runs of 5 (runs may start anywhere in a warp's 32 members)."""
     cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
              "c2_grid_N16_P8": golden_py["c2_grid_N16_P8"], "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"],
              "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"]),
