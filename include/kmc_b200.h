@@ -206,7 +206,7 @@ double kmcb200_measure_peak(int device, int what);
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */
 long long kmcb200_launch_count(void);
 
-/* Name of the hop kernel the calling thread's last kmcb200_run_ensemble launched ("kmc_lanes_kernel",
+/* Name of the hop kernel the last kmcb200_run_ensemble of this process launched ("kmc_lanes_kernel",
  * "kmc_memo_kernel", "kmc_wide_kernel", "kmc_fast_kernel", "kmc_reforder_kernel", "kmc_exact_kernel",
  * "kmc_prob_kernel"; "" before the first call) -- bench.py names the kernel its roofline is about. */
 const char *kmcb200_last_kernel(void);

@@ -71,8 +71,8 @@ extern "C" void kmcb200_set_seed(uint64_t seed) {
     g_next_member.store(0);
 }
 extern "C" long long kmcb200_launch_count(void) { return g_launches.load(); }
-static thread_local const char *g_last_kernel = "";
-extern "C" const char *kmcb200_last_kernel(void) { return g_last_kernel; }
+static std::atomic<const char *> g_last_kernel{""};  // (process-wide: the multi-device entry launches from worker threads)
+extern "C" const char *kmcb200_last_kernel(void) { return g_last_kernel.load(); }
 extern "C" double kmcb200_measure_peak(int device, int what) {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     int launches = 0;
