@@ -21,7 +21,8 @@ import numpy as np  # noqa: E402
 def gpu_rate(w, scale=1.0, reps=2):
     from kmc_dn_b200.ensemble import Layout
     lt = w["tables"]
-    lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R)
+    lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R,
+                 prune_threshold=w.get("prune", 0.0))
     hops = max(1, int(w["hops"] * scale)); pre = int(w["prehops"] * scale)
     kw = dict(basis=lt.basis, prehops=pre, occupation0=w["occupation0"], seed=1)
     lay.run(min(hops, 1000), w["kT"], w["V"], **kw)  # warm-up
@@ -66,6 +67,32 @@ def cpu_rate(w, seconds, semantics="go", use_cache=True, scale=1.0):
     return run(B, hops), B, hops
 
 
+def cpu_rate_pruned(w, seconds, use_cache):
+    """The pruned transition list (simulation.go:200-215, wrapperSimulatePruned) exists only in the single-run port:
+    one trajectory per host thread (ctypes releases the GIL), a strided handful of members."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    lt = w["tables"]
+    n = os.cpu_count() or 1
+    idx = np.linspace(0, len(w["V"]) - 1, n).astype(np.int64)
+    E = lt.E_constant(w["V"][idx])
+
+    def one(k, h):
+        se = np.zeros(lt.N + lt.P); se[lt.N:] = w["V"][idx[k]]
+        oracle.go_simulate(lt.N, lt.P, lt.nu, float(w["kT"][idx[k]]), lt.I_0, lt.R, lt.distances, E[k], lt.transitions_constant,
+                           se, h, variant=1, occupation=w["occupation0"], use_cache=use_cache, cut=w["prune"], seed=k + 1)
+
+    def run(h):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=n) as ex:
+            list(ex.map(lambda k: one(k, h), range(n)))
+        return n * h / (time.perf_counter() - t0)
+
+    r0 = run(200)
+    hops = int(max(200, min(w["hops"], r0 * seconds / n)))
+    return run(hops), n, hops
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tag", default="r01")
@@ -86,6 +113,9 @@ def main():
         ("C3-1e6", workloads.c3_voltage_search(n_controls=64 if q else 1024, seeds=16, hops=1000000), 0.01 if q else 1.0),
         ("C4", workloads.c4_temperature(n_T=64, seeds=64 if q else 1024), 0.1 if q else 1.0),
         ("C5", workloads.c5_scaling(N=256, M=25, B=1024 if q else 8192), 1.0),
+        # C5 with the pruned transition list of validate_tests.py:323 (pairs with tc <= 1e-7 max tc dropped)
+        ("C5-pruned", dict(workloads.c5_scaling(N=256, M=25, B=1024 if q else 8192), prune=1e-7,
+                           name="C5 scaling N=256 P=8, prune_threshold 1e-7"), 1.0),
     ]
     rows = []
     only = [x for x in args.only.split(",") if x]
@@ -97,9 +127,14 @@ def main():
             print(json.dumps(dict(config=name, workload=w["name"], members=int(len(w["V"])), hops=hops, prehops=pre,
                                   gpu_hops_per_s=g, state_cache_miss_rate=miss, finite_fraction=finite)), flush=True)
             continue
-        c_cache, Bc, hc = cpu_rate(w, args.cpu_seconds, "go", True, scale)
-        c_nocache, _, _ = cpu_rate(w, args.cpu_seconds / 2, "go", False, scale)
-        c_py, _, _ = cpu_rate(w, args.cpu_seconds / 2, "py", True, scale)
+        if w.get("prune"):
+            c_cache, Bc, hc = cpu_rate_pruned(w, args.cpu_seconds, True)
+            c_nocache, _, _ = cpu_rate_pruned(w, args.cpu_seconds / 2, False)
+            c_py = float("nan")  # (the numba loop has no pruned list)
+        else:
+            c_cache, Bc, hc = cpu_rate(w, args.cpu_seconds, "go", True, scale)
+            c_nocache, _, _ = cpu_rate(w, args.cpu_seconds / 2, "go", False, scale)
+            c_py, _, _ = cpu_rate(w, args.cpu_seconds / 2, "py", True, scale)
         row = dict(config=name, workload=w["name"], members=int(len(w["V"])), hops=hops, prehops=pre,
                    gpu_hops_per_s=g, state_cache_miss_rate=miss, finite_fraction=finite,
                    cpu_cores=os.cpu_count(), cpu_go_port_cached=c_cache, cpu_go_port_uncached=c_nocache,
