@@ -1,5 +1,5 @@
 // hop_lanes.cu -- production KMC hop loop, ONE THREAD PER TRAJECTORY on the common path (KMCB200_MODE_FAST, N <= 31
-// acceptors, large ensembles).
+// acceptors).
 //
 // Reference semantics being accelerated (MUTUEL/kmc_dn, paths relative to the reference tree):
 //   site energies      goSimulation/simulation.go:226-234, 378-386
@@ -10,160 +10,287 @@
 //   hop + tallies      goSimulation/simulation.go:107-130, 306-319
 //   state cache        goSimulation/simulation.go:222-223, 251-296, 351-412
 //
-// hop_memo.cu (read its header first) runs one trajectory per WARP: a hop that finds its state in the cache still
-// costs 27 warp-instructions.  Here a warp carries 32 trajectories in lock-step, one per thread, and a hop whose
-// state is in the table is plain per-thread code: Philox, one hash, one 64-byte read of the entry's first chunk
-// (header + the 8 most likely events), a branch-free count of thresholds, the mask update -- about 5.5 warp-
-// instructions per hop and trajectory.  Only what is NOT in the table is warp-cooperative: the warp stops, evaluates
-// the missing state of one of its trajectories with the sweep of hop_memo.cu (lane i = acceptor i), parks the result
-// and goes on.  Measured on C3 (1 M members x 1e4 hops, one B200): 6.5e10 hops/s against 2.1e10 of hop_memo.cu;
-// 8.5 warp-instructions per hop against 42.8 (profiles/ncu_r01_v8_lanes_kernel_final.txt).
+// A warp carries 32 trajectories in lock-step, one per thread.  A hop whose state is in the table is plain per-thread
+// code: Philox, one hash, ONE 32-byte read (the state's key, -ln2/total and its 6 most likely events), a select tree,
+// the mask update.  Only what is NOT in the table is warp-cooperative: the warp stops, evaluates the missing state of
+// one of its trajectories (lane i = acceptor i; the sweep of memo_common.cuh) and goes on.
 //
-// Table.  The cumulative rate structure is a PURE function of (layout, E_constant, electrode energies, kT, occupation
-// mask) -- the fp64 energies are exact sums of fp32 terms (hop_memo.cu) -- so trajectories with identical parameters
-// (the seeds of one voltage vector / temperature) SHARE one table: the warp detects the runs of consecutive identical
-// members among its 32 and gives every run one direct-mapped table in global memory (hot entries live in L2; the
-// hardware cache replaces the hand-managed first level of hop_memo.cu).  An entry (512 B) is keyed by the full
-// occupation mask and tagged (launch, first member of the run), so the table is zeroed once and never reset:
+// Round-2 redesign (generation 9).  The round-1 kernel was bound by the L1TEX data pipe (two scattered
+// 256-bit loads per thread and hop = 64 wavefronts per warp-hop, 74 % of the pipe's cycles) and by evaluations caused
+// by CONFLICT misses of its direct-mapped table (a run of 16 seeds visits 60-600 distinct states in 1.6e6 hops, yet
+// 0.26 % of the hops were evaluated).  Now:
 //
-//     0   u32 key | f32 1/total | u32 launch id | u32 first member of the run + 1
-//     16 + 64c   8 x u16   codes of events 8c .. 8c+7: event (partner acceptor j | 32+e hole into electrode e | 64+e
-//                          hole out of electrode e) | acceptor << 7 | (rate > 0) << 12
-//     32 + 64c   8 x u32   their thresholds: inclusive cumulative rate / total in 0.32 fixed point   (c = 0 .. 3)
-//     64  f64 total rate | f64 mass of the slot events
-//     256 32 x f32  per acceptor: mass of its events outside the slots     384 32 x f32  per acceptor: site energy
-//   (the first chunk is read with two 256-bit loads: header + codes, thresholds; the second half of the entry serves
-//    the rest-of-list picks, so that they need no second evaluation of the state)
+// Entry (64 B = two 32-byte sectors), a pure function of (layout, E_constant, electrode energies, kT, occupation mask):
+//     sector A:  u32 key (the mask) | f32 -ln2/total | 6 x u32 event words
+//     sector B:  8 x u32 event words
+//   event word k = F_k << 12 | code_k: the K = 14 LARGEST events of the state in decreasing order (candidates: the 2 or
+//   3 largest events of every acceptor), F_k = q_0 + .. + q_k the cumulative probability in units of 2^-20 with
+//   q_k = floor(rate_k / total * 2^20) -- rounded DOWN; code = acceptor | event << 5 (event: partner acceptor j |
+//   32 + e hole into electrode e | 64 + e hole out of electrode e).  With X = x | 0xfff (x = 32 uniform bits),
+//   X > word_k  <=>  (x >> 12) >= F_k: six compares and five selects resolve a hop.
+//   What the floor leaves over (the events' residuals) and every other event form the TAIL, [F_13 * 2^12, 2^32): a hop
+//   lands there with probability ~3e-5 (C3) and is resolved by evaluating the state again and an exact two-level pick
+//   over the tail list (tail_pick below).  Every event keeps exactly its probability rate / total: front part + residual.
 //
-// The events are the 31 event slots of hop_memo.cu (every acceptor's largest rates), SORTED by decreasing rate: on C3
-// the first chunk answers most hops.  The pick compares the raw 32-bit Philox output x against the thresholds (event k
-// iff thr[k-1] <= x < thr[k]) -- the same partition of [0,1) that hop_memo.cu's fp64 compare against (x+0.5)/2^32
-// realises, in integers.  x >= thr[31] (the mass of all slot events: 0.4 % of the hops on C3 on average, up to 8 % for
-// some voltage vectors) takes the exact two-level pick over the rest of the list (slow_pick below), warp-cooperatively,
-// from the entry's second half.
+// Table.  Trajectories with identical parameters (the seeds of one voltage vector / temperature) SHARE one table: the
+// warp detects the runs of consecutive identical members among its 32; every run gets an equal power-of-two share of
+// the warp slot's sets.  A set is one 128-byte line = 2 ways, LRU: a hit in way 1 swaps the ways, an insertion pushes
+// way 0 to way 1.  (Measured on the CPU model of this table, C3: 2-way LRU with 2048 entries evaluates 0.05 % of the
+// hops where the direct-mapped table with 8192 evaluated 0.3 %.)  The keys are cleared when a warp takes a block of
+// members: no tags, no launch ids, nothing to zero at allocation.
 //
-// Lock-step and misses.  All 32 trajectories of a warp execute hop h together.  Step 1: every thread probes its
-// table (the entry was fetched right after the previous hop); threads that hit resolve their event on their own.
-// Step 2: rest-of-list picks of threads that hit -- they READ entries, so they run before this step writes any.
-// Step 3: for every thread that missed, the warp evaluates the state, writes the entry and resolves from the registers
-// every waiting thread of the run that sits in this very state (an entry may be evicted by the next evaluation of the
-// same step; nobody depends on re-reading it).  Step 4: every thread applies its event.
-// With the table disabled (lanes_flags & 1) every hop takes step 3 -- same arithmetic, bit-identical results (tested).
+// Lock-step.  All 32 trajectories of a warp execute hop h together.  Hot path (inline): way-0 hit in sector A.
+// Everything else goes through lanes_cold(): read phase (per thread: sector B / way 1), then -- behind a warp barrier,
+// so that no read overlaps a write -- way swaps, tail picks and evaluations, one at a time, warp-cooperatively.
+// With the table disabled (lanes_flags & 1) every hop is evaluated -- same arithmetic, bit-identical results (tested).
 //
-// RNG: the same Philox4x32-10 numbering as hop_memo.cu (key = seed, counter = (64-hop block * 32 + pair, global member
-// index), two hops per call), so streams do not depend on batching, on the number of GPUs or on the kernel's geometry.
+// Scheduling.  Work items are (block of 32 members, range of hops).  The first blocks run all their hops in one item;
+// the LAST blocks of the queue are cut into slices of hops (state checkpointed in the output arrays), handed out
+// slice-major with a per-block progress flag, so that the launch does not end on a few warps finishing whole blocks
+// (round 1: SMs active 88 % of the launch).
+//
+// RNG: Philox4x32-10 (key = seed, counter = (64-hop block * 32 + pair, global member index), two hops per call), so
+// streams do not depend on batching, on the number of GPUs or on the kernel's geometry.  The round keys come
+// precomputed from the host (EnsembleDev::rk, constant bank operands).
 #include "memo_common.cuh"
 
 namespace kmcb200 {
 
-#define LENTB 512u  // bytes per table entry
+#define LSETB 128u  // bytes per set (2 ways x 64 B)
 #ifndef LANES_MIN_CTAS
-#define LANES_MIN_CTAS 6  // resident CTAs of 4 warps per SM the register budget is set for
+#define LANES_MIN_CTAS 8  // resident CTAs of 4 warps per SM the register budget is set for
 #endif
+#define LANES_K 14        // events per entry
+#define LANES_RMAX 8      // runs of a warp whose parameters live in shared memory (later runs: from global memory)
+#define LN2F 0.6931471805599453
 
 template <int PT>
 struct LanesGeom {
-    static constexpr int PV = PT > 0 ? PT : 32;   // electrode slots per trajectory
-    static constexpr int MIRB = 256;              // mirror: acceptor energies (128 B) | electrode energies (128 B)
-    static constexpr int EFB = 32 * 32 * 4;       // E_constant (the narrowed fp32 values) of the 32 trajectories
-    static constexpr int VEB = 32 * PV * 4;       // electrode energies of the 32 trajectories
-    static constexpr int TALB = PV * 32 * 4;      // electrode tallies [electrode][trajectory]
-    static constexpr int WARP_BYTES = MIRB + EFB + VEB + TALB;
+    static constexpr int PV = PT > 0 ? PT : 32;             // electrode slots per trajectory
+    static constexpr int MIRB = 256;                        // mirror: acceptor energies (128 B) | electrode energies (128 B)
+    static constexpr int RUNB = 128 + 4 * PV + 16;          // per run: E_constant row (f32 x 32) | electrode energies | -log2e/kT
+    static constexpr int TALB = PV * 32 * 4;                // electrode tallies [electrode][trajectory]
+    static constexpr int WARP_BYTES = MIRB + LANES_RMAX * RUNB + TALB;
 };
 
-__device__ __forceinline__ uint4 ldg_u4(const unsigned char *p) {
-    uint4 v;
-    asm volatile("ld.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
+struct Sector {
+    uint32_t w[8];
+};
+__device__ __forceinline__ Sector ldg_sector(const unsigned char *p) {
+    Sector s;
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(s.w[0]), "=r"(s.w[1]), "=r"(s.w[2]), "=r"(s.w[3]), "=r"(s.w[4]), "=r"(s.w[5]), "=r"(s.w[6]), "=r"(s.w[7])
+                 : "l"(p)
+                 : "memory");
+    return s;
 }
-// header + first chunk (codes, thresholds; 64 B) in ONE statement of two 256-bit loads, issued back to back
-__device__ __forceinline__ void ldg_head(const unsigned char *p, uint4 &h, uint4 &c, uint4 &a, uint4 &b) {
-    asm volatile(
-        "ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
-        "ld.global.v8.u32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%16+32];"
-        : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w), "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w),
-          "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-        : "l"(p)
-        : "memory");
-}
-// codes + thresholds of a later chunk (48 B at p = entry + 64 c + 16)
-__device__ __forceinline__ void ldg_chunk(const unsigned char *p, uint4 &c, uint4 &a, uint4 &b) {
-    asm volatile(
-        "ld.global.v4.u32 {%0, %1, %2, %3}, [%12];\n\t"
-        "ld.global.v8.u32 {%4, %5, %6, %7, %8, %9, %10, %11}, [%12+16];"
-        : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w), "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-        : "l"(p)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t ldg_u16(const unsigned char *p) {
+__device__ __forceinline__ uint32_t ldg_u32(const unsigned char *p) {
     uint32_t v;
-    asm volatile("{ .reg .u16 t; ld.global.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void stg_u4(unsigned char *p, uint4 v) {
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void stg_u32(unsigned char *p, uint32_t v) { asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ float ldg_f32(const unsigned char *p) {
-    float v;
-    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double ldg_f64(const unsigned char *p) {
-    double v;
-    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stg_f32(unsigned char *p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
-__device__ __forceinline__ void stg_f64(unsigned char *p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
-__device__ __forceinline__ void stg_u16(unsigned char *p, uint32_t v) {
-    asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.global.u16 [%0], t; }" ::"l"(p), "r"(v) : "memory");
+// 1 << (n & 31) (BMSK: the code's low 5 bits are the acceptor, no masking needed)
+__device__ __forceinline__ uint32_t bit_wrap(uint32_t n) {
+    uint32_t r;
+    asm("bmsk.wrap.b32 %0, %1, 1;" : "=r"(r) : "r"(n));
+    return r;
 }
 
-// The rest of the list: exact two-level pick over all events EXCEPT the ones that own a slot (x >= mass of the slot
-// events; hop_memo.cu's slow path).  Works on the state's per-acceptor data -- rest_tot (mass outside the slots), e_me
-// (fp32 site energy), code_l (ANY permutation of the slot codes: event | acceptor << 7 | valid << 12) -- either fresh
-// from a sweep or read back from the table entry: the result does not depend on which, nor on the order of the slots.
-// Warp-cooperative (lane = acceptor / target / electrode); returns the event code (event | acceptor << 7), warp-uniform.
-__device__ __noinline__ uint32_t slow_pick(uint32_t occu, uint32_t accm, float nbt, uint32_t x, double total, double mtop,
-                                              float rest_tot, float e_me, float ve_mine, uint32_t code_l, int lane, int N, int P,
-                                              uint32_t a_col_me, uint32_t a_elF_e, uint32_t a_elR_e) {
-    const double rres = ((double)x + 0.5) * 2.3283064365386963e-10 * total - mtop;
-    const double incl = scan_d((double)rest_tot);
+// Philox4x32-10 with the round keys precomputed on the host (rk[2r], rk[2r+1] = key + r * Weyl constants)
+__device__ __forceinline__ uint4 philox_rk(uint4 c, const uint32_t *__restrict__ rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+    }
+    return c;
+}
+
+// event k of a sector's words w[0..n) for X = x | 0xfff (the caller has checked X <= w[n-1], i.e. the event is here)
+__device__ __forceinline__ uint32_t select6(uint32_t X, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f) {
+    const uint32_t s01 = X > a ? b : a, s23 = X > c ? d : c, s45 = X > e ? f : e;
+    return X > d ? s45 : (X > b ? s23 : s01);
+}
+__device__ __forceinline__ uint32_t select8(uint32_t X, const Sector &s) {
+    const uint32_t s01 = X > s.w[0] ? s.w[1] : s.w[0], s23 = X > s.w[2] ? s.w[3] : s.w[2];
+    const uint32_t s45 = X > s.w[4] ? s.w[5] : s.w[4], s67 = X > s.w[6] ? s.w[7] : s.w[6];
+    const uint32_t lo = X > s.w[1] ? s23 : s01, hi = X > s.w[5] ? s67 : s45;
+    return X > s.w[3] ? hi : lo;
+}
+
+// per-warp, per-item constants of the cold path (lives in local memory; the hot loop keeps its own copies in registers)
+struct LaneCtx {
+    uint32_t a_row_me, a_col_me, a_elF, a_elR, a_elF_e, a_elR_e, a_mir, a_run;
+    uint32_t accm, lead_mask;
+    int lane, N, P, hshift;
+    unsigned char *wtab;  // this warp slot's sets
+    int64_t base;         // first member of the block
+    bool use_table;
+};
+
+// parameters of run r (leader = member base + ld): E_constant of acceptor `lane` (narrowed to float32,
+// simulationWrapper.go:50-56), energy of electrode `lane`, -log2(e)/kT
+template <int PT>
+__device__ __forceinline__ void run_params(const EnsembleDev &E, const LaneCtx &c, int r, int ld, double &E64, float &ve_mine, float &nbt) {
+    using G = LanesGeom<PT>;
+    const int lane = c.lane, N = c.N, P = c.P;
+    if (r < LANES_RMAX) {
+        const uint32_t a = c.a_run + (uint32_t)r * G::RUNB;
+        E64 = (double)lds_f(a + lane * 4);
+        ve_mine = (lane < P) ? lds_f(a + 128 + lane * 4) : 0.0f;
+        nbt = lds_f(a + 128 + 4 * G::PV);
+    } else {
+        const int64_t mt = c.base + ld;
+        double e64 = 0.0;
+        if (lane < N) {
+            if (E.E_constant) e64 = E.E_constant[mt * N + lane];
+            else {
+                e64 = E.basis[(int64_t)P * N + lane];
+                for (int p = 0; p < P; ++p) e64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
+            }
+        }
+        E64 = (double)(float)e64;
+        ve_mine = (lane < P) ? (float)E.electrode_v[mt * P + lane] : 0.0f;
+        nbt = -1.4426950408889634f / (float)E.kT[mt];
+    }
+}
+
+// What an evaluation leaves in the registers of the warp: lane k < K holds event k (word = F_k << 12 | code), every lane
+// (= acceptor) its energy, its total rate and its candidates.
+template <int NR>
+struct Eval {
+    double total;      // total rate of the state (warp-uniform)
+    float rtp;         // -ln2 / total
+    uint32_t word;     // lane k < LANES_K: F_k << 12 | code_k, else 0xffffffff
+    uint32_t F13;      // F of the last event (warp-uniform): the tail starts at F13 << 12
+    uint32_t win_q;    // lane k < LANES_K: owner acceptor | q_k << 5
+    float e_me, R;     // this acceptor's fp32 site energy, the sum of all its rates
+};
+
+// Evaluate state occu of a run: sweep, total, the K largest events, their quantised lengths.
+template <int PT, int NR>
+__device__ __forceinline__ bool evaluate_state(const LaneCtx &c, uint32_t occu, double E64, float ve_mine, float nbt, Eval<NR> &ev) {
+    const int lane = c.lane, N = c.N, P = c.P;
+    __syncwarp();
+    if (lane < P) sts_f(c.a_mir + 128 + lane * 4, ve_mine);
+    float rest;
+    float tk[NR];
+    int pk[NR];
+    sweep_state<PT, NR>(occu, c.accm, E64, lane, N, P, nbt, c.a_row_me, c.a_mir, c.a_elF, c.a_elR, ev.e_me, tk, pk, rest);
+    float R = rest;
+#pragma unroll
+    for (int r = NR - 1; r >= 0; --r) R += tk[r];
+    if (lane >= N) R = 0.0f;
+    ev.R = R;
+    double total = (double)R;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) total += __shfl_xor_sync(FULL, total, d);
+    ev.total = total;
+    if (!(total > 0.0)) return false;  // no transition possible (simulation.go:297 would divide by zero)
+    ev.rtp = (float)(-LN2F / total);
+    // candidates of this acceptor: key = rate bits (7 low mantissa bits dropped) | rank << 5 | lane, event codes packed
+    const bool occ_a = (occu >> lane) & 1u;
+    uint32_t keys[NR], evts = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        const uint32_t evt = ((uint32_t)pk[r] < (uint32_t)N) ? (uint32_t)pk[r] : ((uint32_t)pk[r] - (uint32_t)N + (occ_a ? 32u : 64u));
+        evts |= evt << (7 * r);
+        keys[r] = (lane < N && tk[r] > 0.0f) ? ((__float_as_uint(tk[r]) & ~127u) | ((uint32_t)r << 5) | (uint32_t)lane) : 0u;
+    }
+    // the K largest candidates, one REDUX.MAX per event; lane k keeps event k
+    uint32_t head = keys[0], mywk = 0, myev = 0;
+    int ptr = 0;
+#pragma unroll
+    for (int k = 0; k < LANES_K; ++k) {
+        const uint32_t wk = __reduce_max_sync(FULL, head);
+        const int win = (int)(wk & 31u);
+        const uint32_t e = __shfl_sync(FULL, evts, win);
+        if (lane == k) { mywk = wk; myev = e; }
+        if (lane == win) {
+            ++ptr;
+            head = 0u;
+#pragma unroll
+            for (int r = 1; r < NR; ++r)
+                if (ptr == r) head = keys[r];
+        }
+    }
+    // quantised length of event k: q = floor(rate / total * 2^20 * (1 - 2^-24)) from the truncated rate: never more than
+    // the event's true share, and the sum stays below 2^20
+    const double inv20 = 1048575.9375 / total;
+    uint32_t q = 0, code = 0;
+    if (lane < LANES_K && mywk) {
+        const int rank = (int)((mywk >> 5) & 3u);
+        code = (mywk & 31u) | (((myev >> (7 * rank)) & 127u) << 5);
+        q = (uint32_t)__double2uint_rd((double)__uint_as_float(mywk & ~127u) * inv20);
+    }
+    uint32_t F = q;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(FULL, F, d);
+        if (lane >= d) F += t;
+    }
+    ev.F13 = __shfl_sync(FULL, F, LANES_K - 1);
+    ev.word = (lane < LANES_K) ? ((F << 12) | code) : 0xffffffffu;
+    ev.win_q = (code & 31u) | (q << 5);
+    return true;
+}
+
+// The tail: exact two-level pick over every event of the state with the front parts q_k * total / 2^20 of the K front
+// events taken off (x >= F13 << 12).  A pure function of the state and x; warp-cooperative (lane = acceptor / target /
+// electrode); returns the event code (acceptor | event << 5), warp-uniform.
+template <int NR>
+__device__ __noinline__ uint32_t tail_pick(const LaneCtx &c, const Eval<NR> &ev, uint32_t occu, float nbt, float ve_mine, uint32_t x) {
+    const int lane = c.lane, N = c.N, P = c.P;
+    const double unit = ev.total * 9.5367431640625e-07;  // total / 2^20
+    const double u = ((double)(x - (ev.F13 << 12)) + 0.5) * 2.3283064365386963e-10 * ev.total;
+    // first level: acceptors, each with the front parts of its own events removed
+    double mine = (double)ev.R;
+    const uint32_t evcode = ev.word & 4095u;
+    for (int k = 0; k < LANES_K; ++k) {
+        const uint32_t wq = __shfl_sync(FULL, ev.win_q, k);
+        if ((int)(wq & 31u) == lane) mine -= (double)(wq >> 5) * unit;
+    }
+    if (mine < 0.0) mine = 0.0;
+    const double incl = scan_d(mine);
     double ex = __shfl_up_sync(FULL, incl, 1);
     if (lane == 0) ex = 0.0;
-    const uint32_t rpos = __ballot_sync(FULL, rest_tot > 0.0f);
-    uint32_t b2 = __ballot_sync(FULL, ex < rres) & rpos;
-    if (!b2) b2 = rpos & (0u - rpos);
-    const bool valid = (code_l >> 12) & 1u;
-    const uint32_t c12 = code_l & 4095u;
-    // an event that is certainly allowed, for the cases rounding leaves without a pick
-    const uint32_t any_valid = __reduce_max_sync(FULL, valid ? c12 : 0u);
-    if (!b2) return any_valid;  // no mass outside the slots (rounding)
+    const uint32_t pos = __ballot_sync(FULL, mine > 0.0);
+    // an event that is certainly allowed, for the cases rounding leaves without a pick: the largest event of the state
+    const uint32_t fallback = __shfl_sync(FULL, evcode, 0);
+    if (!pos) return fallback;
+    uint32_t b2 = __ballot_sync(FULL, ex < u) & pos;
+    if (!b2) b2 = pos & (0u - pos);
     const int istar = 31 - __clz(b2);
-    const float rf = __shfl_sync(FULL, (float)(rres - ex), istar);
-    // the acceptor's events that own a slot are skipped; the smallest of their codes is the rounding fallback
-    const bool match = valid && (int)((code_l >> 7) & 31u) == istar;
-    const uint32_t evt = code_l & 127u;
-    const uint32_t skipA = __reduce_or_sync(FULL, (match && evt < 32u) ? (1u << evt) : 0u);
-    const uint32_t skipE = __reduce_or_sync(FULL, (match && evt >= 32u) ? (1u << (evt & 31u)) : 0u);
-    uint32_t fallback = __reduce_min_sync(FULL, match ? c12 : 0xffffu);
-    if (fallback == 0xffffu) fallback = any_valid;
-    const bool keepA = !((skipA >> lane) & 1u), keepE = !((skipE >> lane) & 1u);
+    const float rf = __shfl_sync(FULL, (float)(u - ex), istar);
     const bool rowocc = (occu >> istar) & 1u;
-    const float e_star = __shfl_sync(FULL, e_me, istar);
+    const float e_star = __shfl_sync(FULL, ev.e_me, istar);
+    // front parts of istar's events, by target: acceptor target j / electrode e <-> lane
+    float offA = 0.0f, offE = 0.0f;
+    for (int k = 0; k < LANES_K; ++k) {
+        const uint32_t wq = __shfl_sync(FULL, ev.win_q, k);
+        const uint32_t cd = __shfl_sync(FULL, evcode, k);
+        if ((int)(wq & 31u) == istar) {
+            const uint32_t evt = cd >> 5;
+            const float part = (float)((double)(wq >> 5) * unit);
+            if (evt < 32u) {
+                if ((int)evt == lane) offA = part;
+            } else if ((int)(evt & 31u) == lane) offE = part;
+        }
+    }
     int from, to;
     if (rowocc) {
         from = istar;
         to = -1;
         int lastA = -1;
         float sA = 0.0f;
-        const uint32_t emp = ~occu & accm;
+        const uint32_t emp = ~occu & c.accm;
         if (emp) {  // acceptor targets: istar -> empty `lane`
             float rr = 0.0f;
-            if (((emp >> lane) & 1u) && keepA) {
-                const float2 v = lds_f2(a_col_me + istar * 8);
-                rr = ma(v.x, v.y, e_me, e_star, nbt);
+            if ((emp >> lane) & 1u) {
+                const float2 v = lds_f2(c.a_col_me + istar * 8);
+                rr = fmaxf(ma(v.x, v.y, ev.e_me, e_star, nbt) - offA, 0.0f);
             }
             const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
             if (nz) {
@@ -178,7 +305,7 @@ __device__ __noinline__ uint32_t slow_pick(uint32_t occu, uint32_t accm, float n
         }
         if (to < 0) {  // electrode targets: istar -> electrode `lane`
             float rr = 0.0f;
-            if (lane < P && keepE) rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nbt, 0.0f));
+            if (lane < P) rr = fmaxf(lds_f(c.a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nbt, 0.0f)) - offE, 0.0f);
             const int e = pick_group<5>(rr, rf - sA);
             to = (e >= 0) ? N + e : lastA;
         }
@@ -186,21 +313,114 @@ __device__ __noinline__ uint32_t slow_pick(uint32_t occu, uint32_t accm, float n
     } else {  // empty acceptor: events electrode `lane` -> istar
         to = istar;
         float rr = 0.0f;
-        if (lane < P && keepE) rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nbt, 0.0f));
+        if (lane < P) rr = fmaxf(lds_f(c.a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nbt, 0.0f)) - offE, 0.0f);
         from = pick_group<5>(rr, rf);
         if (from < 0) return fallback;
         from += N;
     }
-    if (from < N && to < N) return (uint32_t)to | ((uint32_t)from << 7);
-    if (from < N) return (uint32_t)(32 + to - N) | ((uint32_t)from << 7);
-    return (uint32_t)(64 + from - N) | ((uint32_t)to << 7);
+    if (from < N && to < N) return (uint32_t)from | ((uint32_t)to << 5);
+    if (from < N) return (uint32_t)from | ((uint32_t)(32 + to - N) << 5);
+    return (uint32_t)to | ((uint32_t)(64 + from - N) << 5);
 }
 
-// The entry of the NEXT state is fetched right after a hop is applied: the loads fly while the next hop's variates are
-// generated.  (Measured on C3: 6 resident CTAs per SM beat 5, 7 and 8; two 256-bit loads -- served from L2 -- beat four
-// 128-bit loads that allocate in L1, 6.3e10 against 5.7e10 hops/s.)
+// Everything that is not a way-0 hit in sector A.  st: 0 = nothing to do for this thread, 1 = way 0 holds another state,
+// 2 = way-0 hit, but the event lies beyond sector A (f7 = its last word).  Returns {code, bits of -ln2/total}; bit 31 of
+// the code: the state is dead (no transition possible); bit 30: the state was evaluated for this thread.
 template <int PT, bool DBG, int NR>
-__global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const LayoutDev L, const EnsembleDev E) {
+__device__ __forceinline__ uint2 lanes_cold(const EnsembleDev &E, const LaneCtx &c, uint32_t occ, uint32_t xr, uint32_t st, uint32_t f1,
+                                         uint32_t f7, uint32_t ri, uint32_t setofs, int leader) {
+    const int lane = c.lane;
+    const uint32_t X = xr | 0xfffu;
+    uint32_t code = 0, rt = f1;
+    // ---- read phase (per thread): sector B of way 0, or way 1
+    bool need_eval = false, need_tail = false, want_swap = false;
+    unsigned char *line = c.wtab + (size_t)(setofs + ((occ * 0x9E3779B1u) >> c.hshift)) * LSETB;
+    if (st == 2) {
+        const Sector b = ldg_sector(line + 32);
+        if (X > b.w[7]) need_tail = true;
+        else code = select8(X, b);
+    } else if (st == 1) {
+        if (c.use_table) {
+            const Sector a = ldg_sector(line + 64);
+            if (a.w[0] == occ) {
+                want_swap = true;
+                rt = a.w[1];
+                if (X > a.w[7]) {
+                    const Sector b = ldg_sector(line + 96);
+                    if (X > b.w[7]) need_tail = true;
+                    else code = select8(X, b);
+                } else code = select6(X, a.w[2], a.w[3], a.w[4], a.w[5], a.w[6], a.w[7]);
+            } else need_eval = true;
+        } else need_eval = true;
+    }
+    __syncwarp();  // every read of this step is done before the table is written
+
+    // ---- way swaps (LRU: the way just hit becomes way 0), one set at a time, all lanes move one word each
+    uint32_t swaps = __ballot_sync(FULL, want_swap);
+    while (swaps) {
+        const int t = __ffs(swaps) - 1;
+        unsigned char *ln = (unsigned char *)__shfl_sync(FULL, (unsigned long long)line, t);
+        swaps &= ~__ballot_sync(FULL, want_swap && line == ln);
+        const uint32_t v = ldg_u32(ln + lane * 4);
+        __syncwarp();
+        stg_u32(ln + ((lane * 4) ^ 64), v);
+        __syncwarp();
+    }
+
+    // ---- evaluations (states that are not in the table) and tail picks (states that are, but x lies beyond the front)
+    uint32_t need = __ballot_sync(FULL, need_eval || need_tail);
+    bool died = false, evaluated = false;
+    while (need) {
+        const int t = __ffs(need) - 1;
+        const uint32_t occu = __shfl_sync(FULL, occ, t);
+        const int r = (int)__shfl_sync(FULL, ri, t);
+        double E64;
+        float ve_mine, nbt;
+        run_params<PT>(E, c, r, __shfl_sync(FULL, leader, t), E64, ve_mine, nbt);
+        Eval<NR> ev;
+        const bool ok = evaluate_state<PT, NR>(c, occu, E64, ve_mine, nbt, ev);
+        // threads of this run that wait on this very state (t among them) are all served by this evaluation
+        const uint32_t same = __ballot_sync(FULL, ((need >> lane) & 1u) && occ == occu && ri == (uint32_t)r);
+        need &= ~same;
+        if ((same >> lane) & 1u) evaluated = true;
+        if (!ok) {
+            if ((same >> lane) & 1u) died = true;
+            continue;
+        }
+        const uint32_t ins = __ballot_sync(FULL, need_eval) & same;
+        if (ins && c.use_table) {  // insert: way 0 <- the new entry, way 1 <- the old way 0 (if it held a state)
+            unsigned char *ln = (unsigned char *)__shfl_sync(FULL, (unsigned long long)line, t);
+            const uint32_t v = ldg_u32(ln + (lane & 15) * 4);
+            const uint32_t oldkey = __shfl_sync(FULL, v, 0);
+            __syncwarp();
+            if (oldkey != 0xffffffffu && lane < 16) stg_u32(ln + 64 + lane * 4, v);
+            if (lane < 6) stg_u32(ln + 8 + lane * 4, ev.word);
+            else if (lane < LANES_K) stg_u32(ln + 32 + (lane - 6) * 4, ev.word);
+            else if (lane == LANES_K) stg_u32(ln, occu);
+            else if (lane == LANES_K + 1) stg_u32(ln + 4, __float_as_uint(ev.rtp));
+            __syncwarp();
+        }
+        uint32_t todo = same;
+        while (todo) {
+            const int t2 = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint32_t x2 = __shfl_sync(FULL, xr, t2);
+            const uint32_t bb = __ballot_sync(FULL, (x2 | 0xfffu) <= ev.word);  // lanes >= K hold 0xffffffff
+            const int k = __ffs(bb) - 1;
+            uint32_t c2;
+            if (k < LANES_K) c2 = __shfl_sync(FULL, ev.word, k) & 4095u;
+            else c2 = tail_pick<NR>(c, ev, occu, nbt, ve_mine, x2);
+            if (lane == t2) {
+                code = c2;
+                rt = __float_as_uint(ev.rtp);
+            }
+        }
+    }
+    return make_uint2((code & 4095u) | (died ? 0x80000000u : 0u) | (evaluated ? 0x40000000u : 0u), rt);
+}
+
+template <int PT, bool DBG, int NR>
+__global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const LayoutDev L, const __grid_constant__ EnsembleDev E) {
     using G = LanesGeom<PT>;
     constexpr int PV = G::PV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -226,105 +446,197 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u) + (uint32_t)warp * G::WARP_BYTES;
-    const uint32_t a_mir = wb, a_ef = wb + G::MIRB, a_ve = a_ef + G::EFB, a_tal = a_ve + G::VEB;
-    const uint32_t a_row_me = sb + lane * 8u;         // + j*ROWB     : pair (source lane  -> target j)
-    const uint32_t a_col_me = sb + lane * ROWB;       // + istar*8    : pair (source istar -> target lane)
-    const uint32_t a_elF_e = a_elF + lane * ELB;      // + istar*4    : istar -> electrode lane
-    const uint32_t a_elR_e = a_elR + lane * ELB;      // + istar*4    : electrode lane -> istar
-    const uint32_t accm = (1u << N) - 1u;             // N <= 31
-    // event slots (hop_memo.cu): slot `lane` serves rank sl_r of acceptor sl_a; acceptor `lane` owns n_slots of its ranks
-    const int sl_a = (NR > 1 && lane < 31) ? lane % N : lane;
-    const int sl_r = (NR > 1) ? (lane < 31 ? lane / N : NR) : 0;
-    int n_slots = 1;
-    if (NR > 1) {
-        n_slots = 0;
-        if (lane < N)
-            for (int r = 0; r < NR; ++r) n_slots += (lane + r * N <= 30);
-    }
+    const uint32_t a_mir = wb, a_run = wb + G::MIRB, a_tal = a_run + LANES_RMAX * G::RUNB;
+    LaneCtx ctx;
+    ctx.a_row_me = sb + lane * 8u;    // + j*ROWB     : pair (source lane  -> target j)
+    ctx.a_col_me = sb + lane * ROWB;  // + istar*8    : pair (source istar -> target lane)
+    ctx.a_elF = a_elF;
+    ctx.a_elR = a_elR;
+    ctx.a_elF_e = a_elF + lane * ELB;  // + istar*4    : istar -> electrode lane
+    ctx.a_elR_e = a_elR + lane * ELB;  // + istar*4    : electrode lane -> istar
+    ctx.a_mir = a_mir;
+    ctx.a_run = a_run;
+    ctx.accm = (1u << N) - 1u;  // N <= 31
+    ctx.lane = lane;
+    ctx.N = N;
+    ctx.P = P;
 
-    const int tlog = E.gtab_log;  // log2(table entries per warp slot), >= 6
+    const int tlog = E.gtab_log;  // log2(sets per warp slot), >= 6
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
-    unsigned char *const wtab = E.gtab + ((size_t)wslot << tlog) * LENTB;
+    unsigned char *const wtab = E.gtab + ((size_t)wslot << tlog) * LSETB;
     const bool use_table = !(E.lanes_flags & 1);
-    const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
+    ctx.wtab = wtab;
+    ctx.use_table = use_table;
     const int64_t total_hops = E.prehops + E.hops, prehops = E.prehops;
-    const uint32_t tagx = E.launch_id;
+    const int64_t nblocks = (E.B + 31) >> 5;
+    const int64_t nb_full = E.lanes_nb_full, nb_sl = nblocks - nb_full;
+    const int ns = E.lanes_ns;
+    const int64_t n_items = nb_full + nb_sl * ns;
 
-    // ---- persistent: every warp pulls blocks of 32 members from the global queue
+    // ---- persistent: every warp pulls work items from the global queue
     for (;;) {
         unsigned long long mq = 0;
-        if (lane == 0) mq = atomicAdd(E.queue, 32ULL);
-        const int64_t base = (int64_t)__shfl_sync(FULL, mq, 0);
-        if (base >= E.B) break;
+        if (lane == 0) mq = atomicAdd(E.queue, 1ULL);
+        const int64_t item = (int64_t)__shfl_sync(FULL, mq, 0);
+        if (item >= n_items) break;
+        int64_t blk, hA, hB;
+        int s0 = 0, s1 = ns;
+        if (item < nb_full) {
+            blk = item;
+            hA = 0;
+            hB = total_hops;
+        } else {
+            const int64_t q = item - nb_full;
+            s0 = (int)(q / nb_sl);
+            s1 = s0 + 1;
+            blk = nb_full + q % nb_sl;
+            hA = (int64_t)s0 * E.lanes_slice_hops;
+            hB = (s1 == ns) ? total_hops : (int64_t)s1 * E.lanes_slice_hops;
+        }
+        const bool first = s0 == 0, last = s1 == ns;
+        const int64_t base = blk << 5;
         const int64_t m = base + lane;
         const bool active = m < E.B;
         const int64_t mc = active ? m : E.B - 1;
+        ctx.base = base;
 
-        // ---- member parameters: thread t = trajectory t
-        const float nb = -1.4426950408889634f / (float)E.kT[mc];
-        __syncwarp();
-        for (int e = 0; e < P; ++e) {
-            sts_f(a_ve + (uint32_t)(lane * PV + e) * 4u, active ? (float)E.electrode_v[mc * P + e] : 0.0f);
-            sts_u(a_tal + (uint32_t)e * 128u + lane * 4u, 0u);
-        }
-        uint32_t occ = 0;
-        if (E.occupation0 && active)
-            for (int i = 0; i < N; ++i) occ |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
-        // E_constant of every trajectory, narrowed to float32 (simulationWrapper.go:50-56): row t, lane = acceptor
-        for (int t = 0; t < 32; ++t) {
-            const int64_t mt = base + t;
-            float ef = 0.0f;
-            if (mt < E.B && lane < N) {
-                double E64;
-                if (E.E_constant) E64 = E.E_constant[mt * N + lane];
-                else {
-                    E64 = E.basis[(int64_t)P * N + lane];
-                    for (int p = 0; p < P; ++p) E64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
-                }
-                ef = (float)E64;
-            }
-            sts_f(a_ef + (uint32_t)(t * 32 + lane) * 4u, ef);
-        }
-        __syncwarp();
-
-        // ---- runs of identical members: bit t of sp = member t has the parameters of member t-1
-        uint32_t sp = 0;
+        // ---- runs of identical members: bit t of sp = member t has exactly the parameters of member t-1
+        uint32_t sp;
         {
-            const float nbp = __shfl_up_sync(FULL, nb, 1);
-            const uint32_t spk = __ballot_sync(FULL, !active || (lane > 0 && __float_as_uint(nbp) == __float_as_uint(nb)));
-            for (int t = 1; t < 32; ++t) {
-                bool eq = true;
-                if (lane < N) eq = lds_u(a_ef + (uint32_t)(t * 32 + lane) * 4u) == lds_u(a_ef + (uint32_t)((t - 1) * 32 + lane) * 4u);
-                if (lane < P) eq = eq && lds_u(a_ve + (uint32_t)(t * PV + lane) * 4u) == lds_u(a_ve + (uint32_t)((t - 1) * PV + lane) * 4u);
-                if (__all_sync(FULL, eq) || base + t >= E.B) sp |= 1u << t;
+            bool eq = lane > 0 && active;
+            if (eq) {
+                eq = __double_as_longlong(E.kT[mc]) == __double_as_longlong(E.kT[mc - 1]);
+                for (int p = 0; p < P && eq; ++p)
+                    eq = __double_as_longlong(E.electrode_v[mc * P + p]) == __double_as_longlong(E.electrode_v[(mc - 1) * P + p]);
+                if (E.E_constant)
+                    for (int i = 0; i < N && eq; ++i)
+                        eq = __double_as_longlong(E.E_constant[mc * N + i]) == __double_as_longlong(E.E_constant[(mc - 1) * N + i]);
             }
-            sp &= spk;
+            sp = __ballot_sync(FULL, eq || (!active && lane > 0));
         }
-        // runs of identical members (any length, any alignment): every run of the warp gets the same power-of-two share
-        // of the warp slot's table entries
         const uint32_t lead_mask = ~sp;  // bit l = member l starts a run (bit 0 always does)
         const int leader = 31 - __clz(lead_mask & (0xffffffffu >> (31 - lane)));
         const int nruns = __popc(lead_mask);
-        const int slog = tlog - (nruns > 1 ? 32 - __clz(nruns - 1) : 0);  // log2(table entries per run) >= 1
+        const int slog = tlog - (nruns > 1 ? 32 - __clz(nruns - 1) : 0);  // log2(sets per run) >= 1
         const int hshift = 32 - slog;
-        const uint32_t grp = (uint32_t)leader;
-        const uint32_t gofs = ((uint32_t)__popc(lead_mask & ((1u << leader) - 1u)) << slog) * LENTB;  // (< 2^25: 32 bits)
-        const uint32_t tagy = (uint32_t)(base + leader) + 1u;
-#define LANES_HEAD(p_) ldg_head(p_, hd, tc, ta, tb)
-#define LANES_ENT(mask) (wtab + (size_t)(gofs + (((mask) * 0x9E3779B1u) >> hshift) * LENTB))
+        const uint32_t ri = (uint32_t)__popc(lead_mask & ((1u << leader) - 1u));  // index of this thread's run
+        const uint32_t setofs = ri << slog;
+        ctx.lead_mask = lead_mask;
+        ctx.hshift = hshift;
+#define LANES_SET(mask) (wtab + (size_t)(setofs + (((mask) * 0x9E3779B1u) >> hshift)) * LSETB)
 
-        const uint64_t gm = E.member_index0 + (uint64_t)mc;
+        // ---- parameters of the first runs into shared memory; tallies; empty table
+        __syncwarp();
+        {
+            uint32_t lm = lead_mask;
+            for (int r = 0; r < LANES_RMAX && lm; ++r) {
+                const int ld = __ffs(lm) - 1;
+                lm &= lm - 1;
+                const int64_t mt = base + ld;
+                const uint32_t a = a_run + (uint32_t)r * G::RUNB;
+                float ef = 0.0f;
+                if (lane < N) {
+                    double E64;
+                    if (E.E_constant) E64 = E.E_constant[mt * N + lane];
+                    else {
+                        E64 = E.basis[(int64_t)P * N + lane];
+                        for (int p = 0; p < P; ++p) E64 += E.electrode_v[mt * P + p] * E.basis[(int64_t)p * N + lane];
+                    }
+                    ef = (float)E64;
+                }
+                sts_f(a + lane * 4, ef);
+                if (lane < P) sts_f(a + 128 + lane * 4, (float)E.electrode_v[mt * P + lane]);
+                if (lane == 0) sts_f(a + 128 + 4 * PV, -1.4426950408889634f / (float)E.kT[mt]);
+            }
+        }
+        if (use_table)
+            for (uint32_t s = lane; s < (2u << tlog); s += 32) stg_u32(wtab + (size_t)s * 64u, 0xffffffffu);
+
+        // ---- state: from the inputs (first slice) or from the checkpoint the previous slice left in the outputs
+        uint32_t occ = 0;
         bool alive = active, dead = false;
         double t_acc = 0.0;
-        float t_part = 0.0f;
         long long n_miss = 0;
-        uint4 r = make_uint4(0u, 0u, 0u, 0u);
-        uint4 hd = make_uint4(0u, 0u, 0u, 0u), ta = hd, tb = hd, tc = hd;  // (launch ids start at 1: never a valid header)
-        if (alive && use_table) LANES_HEAD(LANES_ENT(occ));
+        if (first) {
+            for (int e = 0; e < P; ++e) sts_u(a_tal + (uint32_t)e * 128u + lane * 4u, 0u);
+            if (E.occupation0 && active)
+                for (int i = 0; i < N; ++i) occ |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
+        } else {
+            if (lane == 0) {
+                const volatile uint32_t *pr = E.lanes_prog + (blk - nb_full);
+                while (*pr < (uint32_t)s0) __nanosleep(200);
+            }
+            __syncwarp();
+            __threadfence();
+            if (active) {
+                occ = __ldcg(E.lanes_ck + m);
+                t_acc = __ldcg(E.time + m);
+                if (!(t_acc < __longlong_as_double(0x7ff0000000000000LL))) { alive = false; dead = true; }
+                if (DBG && E.misses) n_miss = __ldcg(E.misses + m);
+            }
+            for (int e = 0; e < P; ++e)
+                sts_u(a_tal + (uint32_t)e * 128u + lane * 4u, active ? (uint32_t)__ldcg((const long long *)E.electrode_occ + m * P + e) : 0u);
+        }
+        __syncwarp();
+
+        const uint64_t gm = E.member_index0 + (uint64_t)mc;
+        float t_part = 0.0f;
+        // sector A of way 0 of the current state's set (fetched right after the previous hop was applied)
+        uint32_t f0 = 0xffffffffu, f1 = 0, f2 = 0, f3 = 0, f4 = 0, f5 = 0, f6 = 0, f7 = 0;
+#define LANES_FETCH(mask)                                                                                              \
+    asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"                                            \
+                 : "=r"(f0), "=r"(f1), "=r"(f2), "=r"(f3), "=r"(f4), "=r"(f5), "=r"(f6), "=r"(f7)                     \
+                 : "l"(LANES_SET(mask))                                                                                \
+                 : "memory")
+        if (alive && use_table) LANES_FETCH(occ);
+
+        // one hop of this thread's trajectory: er -> dwell time, xr -> event
+        bool stop = false;
+#define LANES_HOP(er_, xr_, h_)                                                                                        \
+    do {                                                                                                               \
+        const uint32_t xr = (xr_);                                                                                     \
+        const float lg = lg2_approx(fmaf((float)(er_), 2.3283064365386963e-10f, 1.1641532182693481e-10f));            \
+        const uint32_t X = xr | 0xfffu;                                                                                \
+        uint32_t code = select6(X, f2, f3, f4, f5, f6, f7);                                                            \
+        uint32_t rt = f1;                                                                                              \
+        uint32_t st = 0;                                                                                               \
+        if (alive) st = (f0 != occ) ? 1u : (X > f7 ? 2u : 0u);                                                         \
+        if (__any_sync(FULL, st != 0)) {                                                                               \
+            const uint2 r = lanes_cold<PT, DBG, NR>(E, ctx, occ, xr, st, f1, f7, ri, setofs, leader);                  \
+            if (st) {                                                                                                  \
+                code = r.x;                                                                                            \
+                rt = r.y;                                                                                              \
+                if (r.x >> 31) { alive = false; dead = true; }                                                         \
+                if (DBG && ((r.x >> 30) & 1u)) ++n_miss;                                                               \
+            }                                                                                                          \
+            if (!__any_sync(FULL, alive)) { stop = true; break; }                                                      \
+        }                                                                                                              \
+        /* apply (simulation.go:107-130, 306-319): the code's acceptor flips; an acceptor partner flips too; an */    \
+        /* electrode partner gains (32+e) or loses (64+e) one hole */                                                  \
+        if (alive) {                                                                                                   \
+            const uint32_t evt = (code >> 5) & 127u;                                                                   \
+            occ ^= bit_wrap(code) | bit_clamp(evt);                                                                    \
+            if (evt >= 32u) {                                                                                          \
+                const uint32_t a = a_tal + (evt & 31u) * 128u + lane * 4u;                                             \
+                sts_u(a, lds_u(a) + (evt < 64u ? 1u : 0xffffffffu));                                                   \
+            }                                                                                                          \
+            t_part = fmaf(lg, __uint_as_float(rt), t_part);                                                            \
+            if (DBG && E.trace && (h_) >= prehops) {                                                                   \
+                const int site = (int)(code & 31u);                                                                    \
+                int from, to;                                                                                          \
+                if (evt < 32u) { from = site; to = (int)evt; }                                                         \
+                else if (evt < 64u) { from = site; to = N + (int)evt - 32; }                                           \
+                else { from = N + (int)evt - 64; to = site; }                                                          \
+                int32_t *tp = E.trace + (m * E.hops + ((h_) - prehops)) * 2;                                           \
+                tp[0] = from;                                                                                          \
+                tp[1] = to;                                                                                            \
+            }                                                                                                          \
+            if (use_table) LANES_FETCH(occ);                                                                           \
+        }                                                                                                              \
+    } while (0)
 
         // segments: a segment never straddles a 64-hop variate block or the prehops boundary
-        bool stop = false;
-        for (int64_t h0 = 0; h0 < total_hops && !stop;) {
+        for (int64_t h0 = hA; h0 < hB && !stop;) {
             if (h0 == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
                 t_acc = 0.0;
                 t_part = 0.0f;
@@ -334,223 +646,58 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 t_part = 0.0f;
             }
             int64_t hend = (h0 | 63) + 1;
-            if (hend > total_hops) hend = total_hops;
+            if (hend > hB) hend = hB;
             if (h0 < prehops && hend > prehops) hend = prehops;
             const int q0 = (int)(h0 & 63), q1 = q0 + (int)(hend - h0);
             const uint64_t blk0 = (uint64_t)(h0 >> 6) * 32u;
-            for (int q = q0; q < q1; ++q) {
-            // ---- random variates: unit exponential for the dwell time (simulation.go:297), 32 uniform bits for the pick (:164)
-            uint32_t xr, er;
-            if (!(q & 1)) {
-                const uint64_t blk = blk0 + (uint64_t)(q >> 1);
-                r = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), key);
-                er = r.x;
-                xr = r.y;
-            } else {
-                er = r.z;
-                xr = r.w;
+            uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int q = q0; q < q1 && !stop; ++q) {
+                uint32_t er, xq;
+                if (!(q & 1) || q == q0) {  // (q0 odd: second half of a pair whose first hop belonged to the previous segment)
+                    const uint64_t cb = blk0 + (uint64_t)(q >> 1);
+                    r4 = philox_rk(make_uint4((uint32_t)cb, (uint32_t)(cb >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), E.rk);
+                }
+                if (q & 1) { er = r4.z; xq = r4.w; }
+                else { er = r4.x; xq = r4.y; }
+                LANES_HOP(er, xq, h0 + (q - q0));
             }
-            const float ek = -0.6931471805599453f * lg2_approx(fmaf((float)er, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
-
-            // ---- step 1: probe the table; a thread that finds its state resolves its event on its own
-            uint32_t code = 0;
-            float rt = 0.0f;
-            bool hit = false, slow = false;
-            // (thresholds never decrease: the last clause is always true for a valid entry -- it keeps ptxas from
-            //  sinking the threshold loads below the branch, which would cost a second round trip)
-            hit = alive && use_table && hd.x == occ && hd.z == tagx && hd.w == tagy && tb.w >= ta.x;
-            if (hit) {
-                rt = __uint_as_float(hd.y);
-                int c = 0;
-                for (;;) {
-                    if (xr < tb.w) {
-                        const int k = (int)(xr >= ta.x) + (int)(xr >= ta.y) + (int)(xr >= ta.z) + (int)(xr >= ta.w) +
-                                      (int)(xr >= tb.x) + (int)(xr >= tb.y) + (int)(xr >= tb.z);
-                        const uint32_t w2 = (k & 4) ? ((k & 2) ? tc.w : tc.z) : ((k & 2) ? tc.y : tc.x);
-                        code = (k & 1) ? (w2 >> 16) : (w2 & 0xffffu);
-                        break;
-                    }
-                    if (++c == 4) {
-                        slow = true;
-                        break;
-                    }
-                    ldg_chunk(LANES_ENT(occ) + (uint32_t)c * 64u + 16u, tc, ta, tb);
-                }
-            }
-
-            // ---- step 2: rest-of-list picks of threads that hit (from their entries, before this step writes any)
-            uint32_t need = __ballot_sync(FULL, alive && !hit);
-            uint32_t slowm = __ballot_sync(FULL, slow);
-            bool died = false;
-            if (need | slowm) __syncwarp();  // (step 1's reads of the table are ordered before this step's writes)
-            while (slowm) {
-                const int t = __ffs(slowm) - 1;
-                slowm &= slowm - 1;
-                const uint32_t occu = __shfl_sync(FULL, occ, t);
-                const unsigned char *ent = wtab + (size_t)(__shfl_sync(FULL, gofs, t) + ((occu * 0x9E3779B1u) >> hshift) * LENTB);
-                const float rest_tot = ldg_f32(ent + 256 + lane * 4);
-                const float e_me = ldg_f32(ent + 384 + lane * 4);
-                const uint32_t code_l = ldg_u16(ent + 16 + (lane >> 3) * 64 + (lane & 7) * 2);
-                const double total = ldg_f64(ent + 64), mtop = ldg_f64(ent + 72);
-                const float ve_mine = (lane < P) ? lds_f(a_ve + (uint32_t)(t * PV + lane) * 4u) : 0.0f;
-                const uint32_t rcode = slow_pick(occu, accm, __shfl_sync(FULL, nb, t), __shfl_sync(FULL, xr, t), total, mtop, rest_tot, e_me,
-                                                 ve_mine, code_l, lane, N, P, a_col_me, a_elF_e, a_elR_e);
-                if (lane == t) code = rcode;
-            }
-
-            // ---- step 3: warp-cooperative evaluation of the states that are not in the table
-            while (need) {
-                const int t = __ffs(need) - 1;
-                const uint32_t occu = __shfl_sync(FULL, occ, t);
-                const float nbt = __shfl_sync(FULL, nb, t);
-                const double E64 = (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u);
-                float ve_mine = 0.0f;  // electrode `lane` of trajectory t
-                __syncwarp();
-                if (lane < P) {
-                    ve_mine = lds_f(a_ve + (uint32_t)(t * PV + lane) * 4u);
-                    sts_f(a_mir + 128 + lane * 4, ve_mine);
-                }
-                if (DBG && lane == t) ++n_miss;
-                float e_me, rest;
-                float tk[NR];
-                int pk[NR];
-                sweep_state<PT, NR>(occu, accm, E64, lane, N, P, nbt, a_row_me, a_mir, a_elF, a_elR, e_me, tk, pk, rest);
-                // event slots: slot s <-> rank s / N of acceptor s % N (s = 0..30)
-                float sv = tk[0];       // this slot's rate
-                int spn = pk[0];        // ... its partner site
-                float rest_tot = rest;  // this ACCEPTOR's mass outside the slots
-                if (NR > 1) {
-#pragma unroll
-                    for (int rr = 1; rr < NR; ++rr) {
-                        const float tv = __shfl_sync(FULL, tk[rr], sl_a);
-                        const int pv = __shfl_sync(FULL, pk[rr], sl_a);
-                        if (sl_r == rr) { sv = tv; spn = pv; }
-                        if (rr >= n_slots) rest_tot += tk[rr];
-                    }
-                    if (sl_r >= NR) sv = 0.0f;
-                }
-                if (lane == 31) sv = 0.0f;
-                double mtop = (double)sv, total = (double)rest_tot;  // mass of the slot events | of everything
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) {
-                    mtop += __shfl_xor_sync(FULL, mtop, d);
-                    total += __shfl_xor_sync(FULL, total, d);
-                }
-                total += mtop;
-                // threads of this run that wait on this very state (t among them) are all served by this evaluation
-                const uint32_t grp_t = __shfl_sync(FULL, grp, t);
-                uint32_t same = __ballot_sync(FULL, ((need >> lane) & 1u) && occ == occu && grp == grp_t);
-                need &= ~same;
-                if (!(total > 0.0)) {  // no transition possible (simulation.go:297 would divide by zero)
-                    if ((same >> lane) & 1u) { alive = false; dead = true; }
-                    died = true;
-                    continue;
-                }
-                const bool occ_a = (occu >> sl_a) & 1u;
-                // slot code: event | acceptor << 7 | (rate > 0) << 12
-                const uint32_t mycode = (((uint32_t)spn < (uint32_t)N) ? (uint32_t)spn : ((uint32_t)spn - (uint32_t)N + (occ_a ? 32u : 64u))) |
-                                        ((uint32_t)sl_a << 7) | (sv > 0.0f ? 4096u : 0u);
-                const double inv = 1.0 / total;
-                const float rtot = (float)inv;
-                // slots by decreasing rate: bitonic network on (rate bits with the 5 low mantissa bits replaced by
-                // 31 - slot) -- unique keys; the order only decides which events share the first chunk, not the result
-                uint32_t skey = (__float_as_uint(sv) & ~31u) | (uint32_t)(31 - lane);
-#pragma unroll
-                for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-                    for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-                        const uint32_t other = __shfl_xor_sync(FULL, skey, jj);
-                        const bool keepmax = ((lane & jj) == 0) == ((lane & kk) == 0);
-                        skey = keepmax ? max(skey, other) : min(skey, other);
-                    }
-                }
-                const int ssrc = 31 - (int)(skey & 31u);
-                const float ssv = __shfl_sync(FULL, sv, ssrc);
-                const uint32_t scode = __shfl_sync(FULL, mycode, ssrc);
-                const double incl = scan_d((double)ssv);
-                const uint32_t thr = __double2uint_rn(incl * inv * 4294967296.0);  // (saturates at 2^32 - 1)
-                if (use_table) {
-                    const uint32_t tagy_t = __shfl_sync(FULL, tagy, t);
-                    unsigned char *ent = wtab + (size_t)(__shfl_sync(FULL, gofs, t) + ((occu * 0x9E3779B1u) >> hshift) * LENTB);
-                    unsigned char *ch = ent + (uint32_t)(lane >> 3) * 64u;
-                    stg_u32(ch + 32 + (lane & 7) * 4, thr);
-                    stg_u16(ch + 16 + (lane & 7) * 2, scode);
-                    stg_f32(ent + 256 + lane * 4, rest_tot);
-                    stg_f32(ent + 384 + lane * 4, e_me);
-                    if (lane == 0) {
-                        stg_f64(ent + 64, total);
-                        stg_f64(ent + 72, mtop);
-                        stg_u4(ent, make_uint4(occu, __float_as_uint(rtot), tagx, tagy_t));
-                    }
-                    __syncwarp();
-                }
-                while (same) {
-                    const int t2 = __ffs(same) - 1;
-                    same &= same - 1;
-                    const uint32_t x2 = __shfl_sync(FULL, xr, t2);
-                    const uint32_t bb = __ballot_sync(FULL, x2 < thr);
-                    uint32_t c2;
-                    if (bb) c2 = __shfl_sync(FULL, scode, __ffs(bb) - 1);
-                    else c2 = slow_pick(occu, accm, nbt, x2, total, mtop, rest_tot, e_me, ve_mine, mycode, lane, N, P, a_col_me, a_elF_e, a_elR_e);
-                    if (lane == t2) {
-                        code = c2;
-                        rt = rtot;
-                    }
-                }
-            }
-            if (died && !__any_sync(FULL, alive)) {
-                stop = true;
-                break;
-            }
-
-            // ---- step 4: apply (simulation.go:107-130, 306-319): the slot's acceptor flips; an acceptor partner flips
-            //      too; an electrode partner gains (32+e) or loses (64+e) one hole
-            if (alive) {
-                const uint32_t site = (code >> 7) & 31u, evt = code & 127u;
-                occ ^= (1u << site) | bit_clamp(evt);
-                if (evt >= 32u) {
-                    const uint32_t a = a_tal + (evt & 31u) * 128u + lane * 4u;
-                    sts_u(a, lds_u(a) + (evt < 64u ? 1u : 0xffffffffu));
-                }
-                t_part = fmaf(ek, rt, t_part);
-                if (DBG && E.trace && h0 >= prehops) {
-                    int from, to;
-                    if (evt < 32u) { from = (int)site; to = (int)evt; }
-                    else if (evt < 64u) { from = (int)site; to = N + (int)evt - 32; }
-                    else { from = N + (int)evt - 64; to = (int)site; }
-                    int32_t *tp = E.trace + (m * E.hops + (h0 + (q - q0) - prehops)) * 2;
-                    tp[0] = from;
-                    tp[1] = to;
-                }
-                if (use_table) LANES_HEAD(LANES_ENT(occ));
-            }
-            }  // hops of the segment
             h0 = hend;
         }
+#undef LANES_HOP
+#undef LANES_FETCH
 
-        // ---- results
+        // ---- results (last slice) or checkpoint
         t_acc += (double)t_part;
         if (dead) t_acc = __longlong_as_double(0x7ff0000000000000LL);  // +inf, as time_step = e/0 would give
         __syncwarp();
         if (active) {
             E.time[m] = t_acc;
             for (int e = 0; e < P; ++e) E.electrode_occ[m * P + e] = (int64_t)(int32_t)lds_u(a_tal + (uint32_t)e * 128u + lane * 4u);
-            if (E.occupation_out)
-                for (int i = 0; i < N; ++i) E.occupation_out[m * N + i] = (occ >> i) & 1u;
             if (DBG && E.misses) E.misses[m] = n_miss;
+            if (!last) E.lanes_ck[m] = occ;
+            else if (E.occupation_out)
+                for (int i = 0; i < N; ++i) E.occupation_out[m * N + i] = (occ >> i) & 1u;
         }
-        if (E.site_energies_out) {
+        if (last && E.site_energies_out) {
             for (int t = 0; t < 32; ++t) {
                 const int64_t mt = base + t;
+                if (mt >= E.B) break;
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
-                if (mt >= E.B) continue;
-                if (lane < N)
-                    E.site_energies_out[mt * S + lane] = energy_of(occu, accm, (double)lds_f(a_ef + (uint32_t)(t * 32 + lane) * 4u), a_row_me);
-                if (lane < P) E.site_energies_out[mt * S + N + lane] = (double)lds_f(a_ve + (uint32_t)(t * PV + lane) * 4u);
+                double E64;
+                float ve_t, nbt;
+                run_params<PT>(E, ctx, (int)__shfl_sync(FULL, ri, t), __shfl_sync(FULL, leader, t), E64, ve_t, nbt);
+                if (lane < N) E.site_energies_out[mt * S + lane] = energy_of(occu, ctx.accm, E64, ctx.a_row_me);
+                if (lane < P) E.site_energies_out[mt * S + N + lane] = (double)ve_t;
             }
         }
+        if (!last) {
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicExch(E.lanes_prog + (blk - nb_full), (uint32_t)s1);
+        }
         __syncwarp();
-    }  // blocks of members
+#undef LANES_SET
+    }  // work items
 }
 
 template <int PT>
@@ -559,14 +706,13 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
     const bool dbg = E.trace || E.misses;
     const int warps = 4;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
-    // ranked events per acceptor: as many as the 31 slots hold (3 for N <= 10, 2 up to N = 24, else 1)
-    const int nr = L.N <= 10 ? 3 : (L.N <= 24 ? 2 : 1);
+    // candidates per acceptor for the K largest events of a state
+    const int nr = L.N <= 12 ? 3 : 2;
     auto kern = nr == 3 ? (dbg ? kmc_lanes_kernel<PT, true, 3> : kmc_lanes_kernel<PT, false, 3>)
-              : nr == 2 ? (dbg ? kmc_lanes_kernel<PT, true, 2> : kmc_lanes_kernel<PT, false, 2>)
-                        : (dbg ? kmc_lanes_kernel<PT, true, 1> : kmc_lanes_kernel<PT, false, 1>);
+                        : (dbg ? kmc_lanes_kernel<PT, true, 2> : kmc_lanes_kernel<PT, false, 2>);
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
-    // persistent CTAs: as many as stay resident; every warp loops over blocks of 32 members
+    // persistent CTAs: as many as stay resident; every warp loops over work items
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -585,7 +731,7 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
 }
 
 // plan != nullptr: only report the launch geometry (number of persistent warp slots) -- the caller sizes the table
-// E.gtab = warp_slots * 2^E.gtab_log * 512 bytes from it.
+// E.gtab = warp_slots * 2^E.gtab_log sets of 128 bytes and the slicing of the queue's tail from it.
 cudaError_t launch_lanes(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan) {
     if (E.B <= 0) {
         if (plan) plan->warp_slots = 0;

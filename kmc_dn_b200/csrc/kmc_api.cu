@@ -50,11 +50,20 @@ struct kmcb200_layout {
     void *gtab = nullptr;
     size_t gtab_bytes = 0;
     uint32_t launch_id = 0;  // tag of the second-level entries (kmc_internal.cuh)
-    // state table of the thread-per-trajectory kernel (hop_lanes.cu: warp_slots x 2^tlog x 512 B), grow-only
+    // state table of the thread-per-trajectory kernel (hop_lanes.cu: warp_slots x 2^tlog sets of 128 B), grow-only; the
+    // kernel clears the keys it is about to use, so the table is never zeroed by the host
     void *ltab = nullptr;
     size_t ltab_bytes = 0;
-    uint32_t lanes_launch_id = 0;
+    // hop_lanes.cu: occupation masks between the hop slices of a block + per-block progress flags, grow-only
+    void *lscr = nullptr;
+    size_t lscr_bytes = 0;
     unsigned long long *queue = nullptr;  // member work queue of the persistent kernel
+    // One launch in flight per layout: queue, workspace and tables are per layout, so a call waits (on the device, not on
+    // the host) for the previous call's kernel before it touches them -- also when the two calls use different streams.
+    cudaEvent_t busy = nullptr;
+    bool busy_recorded = false;
+    int pins = 0;             // layout cache: calls currently using this layout (never evicted while > 0)
+    unsigned long long last_use = 0;
     std::mutex mu;
 };
 
@@ -174,8 +183,11 @@ extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     cudaFree(lay->dev.tbl); cudaFree(lay->dev.tblf); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
     cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
     cudaFree(lay->ws);
+    if (lay->busy_recorded) cudaEventSynchronize(lay->busy);
+    if (lay->busy) cudaEventDestroy(lay->busy);
     cudaFree(lay->gtab);
     cudaFree(lay->ltab);
+    cudaFree(lay->lscr);
     cudaFree(lay->queue);
     delete lay;
 }
@@ -193,8 +205,10 @@ struct Carver {  // bump allocator over the layout workspace, 256-byte aligned
 size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 }  // namespace
 
-// MODE_FAST, N <= 31: ensembles of at least this many members run on the thread-per-trajectory kernel (hop_lanes.cu)
-static const int64_t kLanesAutoMinB = 65536;
+// MODE_FAST, N <= 31: ensembles of at least this many members run on the thread-per-trajectory kernel (hop_lanes.cu);
+// its electrode tallies are 32-bit, so runs of 2^31 hops or more stay on the warp-per-trajectory kernels
+static const int64_t kLanesAutoMinB = 24576;
+static const int64_t kLanesMaxHops = (int64_t)1 << 31;
 
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
     if (!lay || !a) return fail("kmcb200_run_ensemble: null argument");
@@ -226,6 +240,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     std::lock_guard<std::mutex> lock(lay->mu);
     CU(cudaSetDevice(lay->device));
     cudaStream_t st = (cudaStream_t)a->stream;
+    if (!lay->busy) CU(cudaEventCreateWithFlags(&lay->busy, cudaEventDisableTiming));
+    if (lay->busy_recorded) CU(cudaStreamWaitEvent(st, lay->busy, 0));  // (a no-op for the stream that recorded it)
     const LayoutDev &D = lay->dev;
     const int N = D.N, P = D.P, S = D.S;
     const int64_t B = a->B, H = a->prehops + a->hops;
@@ -261,7 +277,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         if (a->prob_electrode_occ) need += a256(sizeof(double) * B * P);
     }
     if (need > lay->ws_bytes) {
-        if (lay->ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ws)); lay->ws = nullptr; lay->ws_bytes = 0; }
+        if (lay->ws) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ws)); lay->ws = nullptr; lay->ws_bytes = 0; }  // (st waits on `busy`)
         CU(cudaMalloc(&lay->ws, need));
         lay->ws_bytes = need;
     }
@@ -325,9 +341,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         //      (below that the warp-per-trajectory kernel has more parallelism to offer)
         bool lanes = false;
         {
-            const bool lanes_ok = narrow && !E.stream_e && !E.avg_occupation && !E.traffic;
+            const bool lanes_ok = narrow && !E.stream_e && !E.avg_occupation && !E.traffic && th < kLanesMaxHops;
             if (a->flags & KMCB200_FLAG_LANES) {
-                if (!lanes_ok) return fail("kmcb200_run_ensemble: the thread-per-trajectory kernel needs N <= 31 and has no record / injected-stream outputs");
+                if (!lanes_ok) return fail("kmcb200_run_ensemble: the thread-per-trajectory kernel needs N <= 31, fewer than 2^31 hops and has no record / injected-stream outputs");
                 lanes = true;
             } else if (!(a->flags & KMCB200_FLAG_NO_LANES) && lanes_ok) {
                 lanes = B >= kLanesAutoMinB && !(a->flags & KMCB200_FLAG_NO_MEMO);
@@ -336,17 +352,43 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         }
         if (lanes) {
             E.lanes_flags = (a->flags & KMCB200_FLAG_NO_MEMO) ? 1 : 0;
+            for (int r = 0; r < 10; ++r) {  // Philox4x32 key schedule
+                E.rk[2 * r] = (uint32_t)a->seed + (uint32_t)r * 0x9E3779B9u;
+                E.rk[2 * r + 1] = (uint32_t)(a->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+            }
+            MemoPlan plan{0};
+            le = launch_lanes(D, E, st, nullptr, &plan);
+            if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
+            const int64_t W = plan.warp_slots, nblocks = (B + 31) / 32;
+            // ---- the tail of the queue in slices of hops (hop_lanes.cu, "Scheduling"): with more than one round of blocks
+            //      per warp slot the launch would otherwise end on a few warps finishing whole blocks
+            E.lanes_nb_full = nblocks; E.lanes_ns = 1; E.lanes_slice_hops = th; E.lanes_prog = nullptr; E.lanes_ck = nullptr;
+            int ns = (int)std::min<int64_t>(8, th / 8192);
+            if (const char *ev = getenv("KMCB200_LANES_SLICES")) ns = atoi(ev);
+            if (ns > 1 && nblocks > W) {
+                const int64_t nb_sl = nblocks < 3 * W ? nblocks : 2 * W;
+                E.lanes_nb_full = nblocks - nb_sl; E.lanes_ns = ns;
+                E.lanes_slice_hops = ((th + ns - 1) / ns + 63) / 64 * 64;
+                const size_t need_scr = a256(sizeof(uint32_t) * (size_t)B) + a256(sizeof(uint32_t) * (size_t)nb_sl);
+                if (need_scr > lay->lscr_bytes) {
+                    if (lay->lscr) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->lscr)); lay->lscr = nullptr; lay->lscr_bytes = 0; }
+                    CU(cudaMalloc(&lay->lscr, need_scr));
+                    lay->lscr_bytes = need_scr;
+                }
+                E.lanes_ck = (uint32_t *)lay->lscr;
+                E.lanes_prog = (uint32_t *)((char *)lay->lscr + a256(sizeof(uint32_t) * (size_t)B));
+                CU(cudaMemsetAsync(E.lanes_prog, 0, sizeof(uint32_t) * (size_t)nb_sl, st));
+            }
             E.gtab = nullptr; E.gtab_log = 6;
             if (!(E.lanes_flags & 1)) {
-                // table entries per warp slot (shared by the warp's runs of identical members: a run of g gets g/32 of them)
-                int tlog = th < 3000 ? 11 : (th < 10000 ? 13 : 14);
+                // sets (2 ways x 64 B) per warp slot, shared by the warp's runs of identical members (a run of g members gets
+                // g/32 of them).  A run of 16 seeds visits 60-600 states in 1.6e6 hops; with 2-way LRU sets 2^11 per run
+                // leave next to no conflict misses (profiles/r02/table_model.md)
+                int tlog = th < 3000 ? 9 : (th < 30000 ? 11 : 12);
                 if (const char *ev = getenv("KMCB200_LTAB_LOG")) tlog = atoi(ev);
                 if (tlog < 6) tlog = 6;
                 if (tlog > 16) tlog = 16;
-                MemoPlan plan{0};
-                le = launch_lanes(D, E, st, nullptr, &plan);
-                if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-                size_t bytes = ((size_t)plan.warp_slots << tlog) * 512;
+                size_t bytes = ((size_t)W << tlog) * 128;
                 if (bytes > lay->ltab_bytes) {
                     if (lay->ltab) { CU(cudaStreamSynchronize(st)); CU(cudaFree(lay->ltab)); lay->ltab = nullptr; lay->ltab_bytes = 0; }
                     while (tlog >= 6 && cudaMalloc(&lay->ltab, bytes) != cudaSuccess) {  // a cache: halve it until it fits
@@ -355,20 +397,11 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                         --tlog;
                         bytes >>= 1;
                     }
-                    if (tlog >= 6) {
-                        lay->ltab_bytes = bytes;
-                        CU(cudaMemsetAsync(lay->ltab, 0, bytes, st));  // once: launch id 0 never matches
-                        lay->lanes_launch_id = 0;
-                    }
+                    if (tlog >= 6) lay->ltab_bytes = bytes;
                 }
-                if (tlog >= 6) {
-                    if (++lay->lanes_launch_id == 0) {
-                        CU(cudaMemsetAsync(lay->ltab, 0, lay->ltab_bytes, st));
-                        lay->lanes_launch_id = 1;
-                    }
-                    // (a table left over from a larger launch is simply used at the requested size)
-                    E.gtab = (unsigned char *)lay->ltab; E.gtab_log = tlog; E.launch_id = lay->lanes_launch_id;
-                } else if (a->flags & KMCB200_FLAG_LANES) return fail("kmcb200_run_ensemble: no device memory for the state table");
+                // (a table left over from a larger launch is simply used at the requested size)
+                if (tlog >= 6) { E.gtab = (unsigned char *)lay->ltab; E.gtab_log = tlog; }
+                else if (a->flags & KMCB200_FLAG_LANES) return fail("kmcb200_run_ensemble: no device memory for the state table");
                 else lanes = false;
             }
         }
@@ -419,6 +452,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
     } else { le = launch_fast(D, E, st, &launches); g_last_kernel = "kmc_fast_kernel"; }
     g_launches += launches;
     if (le != cudaSuccess) return fail(std::string("kernel launch: ") + cudaGetErrorString(le));
+    CU(cudaEventRecord(lay->busy, st));
+    lay->busy_recorded = true;
 
     if (!dev_ptrs) {
 #define D2H(field, T, count)                                                                           \
@@ -489,6 +524,10 @@ extern "C" int kmcb200_probe_rates(kmcb200_layout *lay, const double *E_constant
     CU(cudaSetDevice(lay->device));
     const int N = lay->dev.N, P = lay->dev.P, S = lay->dev.S;
     double *dE = nullptr, *dV = nullptr; uint8_t *dO = nullptr; float *dS = nullptr, *dR = nullptr;
+    struct Free {  // the probe's device buffers go away on every return path
+        double *&a, *&b; uint8_t *&c; float *&d, *&e;
+        ~Free() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(d); cudaFree(e); }
+    } free_all{dE, dV, dO, dS, dR};
     CU(cudaMalloc(&dE, sizeof(double) * (N + 1))); CU(cudaMalloc(&dV, sizeof(double) * (P + 1)));
     CU(cudaMalloc(&dO, N + 1)); CU(cudaMalloc(&dS, sizeof(float) * S)); CU(cudaMalloc(&dR, sizeof(float) * S * S));
     CU(cudaMemcpy(dE, E_constant, sizeof(double) * N, cudaMemcpyHostToDevice));
@@ -501,7 +540,6 @@ extern "C" int kmcb200_probe_rates(kmcb200_layout *lay, const double *E_constant
     if (le != cudaSuccess) return fail(std::string("probe launch: ") + cudaGetErrorString(le));
     CU(cudaMemcpy(site_energies_io, dS, sizeof(float) * S, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(rates_out, dR, sizeof(float) * S * S, cudaMemcpyDeviceToHost));
-    cudaFree(dE); cudaFree(dV); cudaFree(dO); cudaFree(dS); cudaFree(dR);
     return 0;
 }
 
@@ -509,38 +547,77 @@ extern "C" int kmcb200_probe_rates(kmcb200_layout *lay, const double *E_constant
 namespace {
 
 // Layout cache: the reference's callers pass the same tables over and over (dn_search.py:107-118,
-// voltage_search.py:138-157); keep the device copies keyed by content.
+// voltage_search.py:138-157); keep the device copies keyed by content.  LRU with pins: a layout handed out by
+// cached_layout() is pinned until unpin_layout() and is never evicted while pinned; eviction removes single
+// least-recently-used entries once the cache holds more than kCacheMaxEntries layouts or kCacheMaxBytes of device memory.
 struct LayoutKey {
     int N, P; double nu, I_0, R, cut; uint64_t h1, h2; int device, pad_;
     bool operator<(const LayoutKey &o) const { return memcmp(this, &o, sizeof(LayoutKey)) < 0; }
 };
 std::mutex g_cache_mu;
 std::map<LayoutKey, kmcb200_layout *> g_cache;
+unsigned long long g_cache_clock = 0;
+const size_t kCacheMaxEntries = 64;
+const size_t kCacheMaxBytes = (size_t)8 << 30;
 
-uint64_t fnv(const double *p, size_t n, uint64_t h) {
-    const unsigned char *b = reinterpret_cast<const unsigned char *>(p);
-    for (size_t i = 0; i < n * sizeof(double); ++i) { h ^= b[i]; h *= 0x100000001b3ULL; }
-    return h;
+// 64-bit words, two independent multiply-xorshift streams (the tables are arrays of doubles)
+void hash_tables(const double *d, const double *tc, size_t n, uint64_t &h1, uint64_t &h2) {
+    uint64_t a = 0xcbf29ce484222325ULL, b = 0x84222325cbf29ce4ULL;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t x, y;
+        memcpy(&x, d + i, 8);
+        memcpy(&y, tc + i, 8);
+        a = (a ^ x) * 0x9E3779B97F4A7C15ULL; a ^= a >> 29;
+        b = (b ^ y) * 0xC2B2AE3D27D4EB4FULL; b ^= b >> 31;
+    }
+    h1 = a; h2 = b;
 }
 
+size_t layout_bytes(const kmcb200_layout *l) { return l->ws_bytes + l->gtab_bytes + l->ltab_bytes + l->lscr_bytes + ((size_t)l->dev.S * l->dev.S) * 48; }
+
+// Returns the cached (or new) layout, PINNED; nullptr on failure.
 kmcb200_layout *cached_layout(int N, int P, const double *d, const double *tc, double nu, double I_0, double R, double cut,
                               int device = 0) {
     const size_t SS = (size_t)(N + P) * (N + P);
     LayoutKey k;
     memset(&k, 0, sizeof(k));
     k.N = N; k.P = P; k.nu = nu; k.I_0 = I_0; k.R = R; k.cut = cut; k.device = device;
-    k.h1 = fnv(d, SS, 0xcbf29ce484222325ULL); k.h2 = fnv(tc, SS, 0x84222325cbf29ce4ULL);
+    hash_tables(d, tc, SS, k.h1, k.h2);
     std::lock_guard<std::mutex> lock(g_cache_mu);
     auto it = g_cache.find(k);
-    if (it != g_cache.end()) return it->second;
-    if (g_cache.size() >= 64) {
-        for (auto &kv : g_cache) kmcb200_layout_destroy(kv.second);
-        g_cache.clear();
+    if (it != g_cache.end()) {
+        ++it->second->pins;
+        it->second->last_use = ++g_cache_clock;
+        return it->second;
+    }
+    // evict unpinned entries, least recently used first, while over the limits
+    for (;;) {
+        size_t bytes = 0;
+        for (auto &kv : g_cache) bytes += layout_bytes(kv.second);
+        if (g_cache.size() < kCacheMaxEntries && bytes < kCacheMaxBytes) break;
+        auto victim = g_cache.end();
+        for (auto jt = g_cache.begin(); jt != g_cache.end(); ++jt)
+            if (jt->second->pins == 0 && (victim == g_cache.end() || jt->second->last_use < victim->second->last_use)) victim = jt;
+        if (victim == g_cache.end()) break;  // everything is in use: grow
+        kmcb200_layout_destroy(victim->second);  // (waits for the layout's last launch)
+        g_cache.erase(victim);
     }
     kmcb200_layout *lay = kmcb200_layout_create(device, N, P, d, tc, nu, I_0, R, cut);
-    if (lay) g_cache[k] = lay;
+    if (lay) {
+        lay->pins = 1;
+        lay->last_use = ++g_cache_clock;
+        g_cache[k] = lay;
+    }
     return lay;
 }
+void unpin_layout(kmcb200_layout *lay) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (lay && lay->pins > 0) --lay->pins;
+}
+struct PinGuard {
+    std::vector<kmcb200_layout *> held;
+    ~PinGuard() { for (auto *l : held) unpin_layout(l); }
+};
 
 [[noreturn]] void die(const char *where) {
     // The reference has no error channel across the FFI (Go panics abort the process).
@@ -560,6 +637,7 @@ double run_single(const char *name, long long NSites, long long NElectrodes, dou
     }
     kmcb200_layout *lay = cached_layout(N, P, distances.data, transitions_constant.data, nu, I_0, R, cut);
     if (!lay) die(name);
+    PinGuard pin; pin.held.push_back(lay);
     double time = 0.0;
     std::vector<int64_t> eo(P > 0 ? P : 1, 0);
     kmcb200_ensemble_args a;
@@ -621,6 +699,7 @@ extern "C" double wrapperSimulateProbability(long long NSites, long long NElectr
     }
     kmcb200_layout *lay = cached_layout(N, P, distances.data, transitions_constant.data, nu, I_0, R, 0.0);
     if (!lay) die(name);
+    PinGuard pin; pin.held.push_back(lay);
     double time = 0.0;
     std::vector<double> se(S > 0 ? S : 1, 0.0);
     kmcb200_ensemble_args a;
@@ -659,14 +738,37 @@ extern "C" long long parallelSimulations(GoSlice NSites, GoSlice NElectrodes, Go
         s.offS = tS; s.offE = tE; s.offC = tC; s.offSE = tS + tE;
         tS += s.N; tE += s.P; tC += (size_t)(s.N + s.P) * (s.N + s.P);
     }
-    // group simulations that share a layout + hop count; each group is one ensemble launch
+    // group simulations that share a layout + hop count; each group is one ensemble launch.  The reference's callers
+    // append the same dn's tables over and over (voltage_search.py:138-157: one dn x 4 tests, `parallel` dns per call),
+    // so a simulation whose tables are byte-identical to its predecessor's (one memcmp) takes the predecessor's layout;
+    // otherwise the tables are hashed once (64-bit words) and looked up in the process-wide cache.  Every layout used by
+    // this call stays pinned until the call returns.
+    PinGuard pins;
     std::map<std::pair<kmcb200_layout *, long long>, std::vector<long long>> groups;
-    for (long long i = 0; i < B; ++i) {
-        const Sim &s = sims[(size_t)i];
-        kmcb200_layout *lay = cached_layout(s.N, s.P, distances.data + s.offC, transitions_constant.data + s.offC,
-                                            nu.data[i], I_0.data[i], R.data[i], 0.0);
-        if (!lay) die("parallelSimulations");
-        groups[{lay, s.hops}].push_back(i);
+    {
+        kmcb200_layout *prev = nullptr;
+        long long pi = -1;
+        for (long long i = 0; i < B; ++i) {
+            const Sim &s = sims[(size_t)i];
+            const size_t SS = (size_t)(s.N + s.P) * (s.N + s.P);
+            kmcb200_layout *lay = nullptr;
+            if (prev) {
+                const Sim &q = sims[(size_t)pi];
+                if (q.N == s.N && q.P == s.P && nu.data[i] == nu.data[pi] && I_0.data[i] == I_0.data[pi] && R.data[i] == R.data[pi] &&
+                    !memcmp(distances.data + s.offC, distances.data + q.offC, SS * sizeof(double)) &&
+                    !memcmp(transitions_constant.data + s.offC, transitions_constant.data + q.offC, SS * sizeof(double)))
+                    lay = prev;
+            }
+            if (!lay) {
+                lay = cached_layout(s.N, s.P, distances.data + s.offC, transitions_constant.data + s.offC, nu.data[i], I_0.data[i],
+                                    R.data[i], 0.0);
+                if (!lay) die("parallelSimulations");
+                pins.held.push_back(lay);
+                prev = lay;
+                pi = i;
+            }
+            groups[{lay, s.hops}].push_back(i);
+        }
     }
     for (auto &g : groups) {
         kmcb200_layout *lay = g.first.first;
@@ -701,6 +803,7 @@ extern "C" long long parallelSimulations(GoSlice NSites, GoSlice NElectrodes, Go
                 lays[(size_t)dv] = cached_layout(N, P, distances.data + s0.offC, transitions_constant.data + s0.offC,
                                                  nu.data[idx[0]], I_0.data[idx[0]], R.data[idx[0]], 0.0, dv);
                 if (!lays[(size_t)dv]) die("parallelSimulations");
+                pins.held.push_back(lays[(size_t)dv]);
             }
             if (kmcb200_run_ensemble_multi(lays.data(), use, &a)) die("parallelSimulations");
         } else if (kmcb200_run_ensemble(lay, &a)) die("parallelSimulations");

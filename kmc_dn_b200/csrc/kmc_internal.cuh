@@ -41,11 +41,20 @@ struct EnsembleDev {
     double *prob_occupation, *prob_electrode_occ;  // MODE_PROB: fractional occupations [B,N], electrode tallies [B,P]
     double *scratch;   // replay kernels: [B][S*S] doubles (rate / cumulative list)
     unsigned long long *queue;  // memoised kernel: member work queue (zeroed before the launch)
-    unsigned char *gtab;  // memoised kernels: second-level cache, warp_slots * 2^gtab_log entries of 288 / 448 B (or null)
-    int gtab_log;         // log2(entries per warp slot); 0 = no second level
+    unsigned char *gtab;  // memoised kernels: second-level cache, warp_slots * 2^gtab_log entries of 288 / 448 B (or null);
+                          // hop_lanes.cu: the state table, warp_slots * 2^gtab_log sets of 128 B
+    int gtab_log;         // log2(entries / sets per warp slot); 0 = no second level
     int lanes_flags;      // hop_lanes.cu: bit 0 = do not consult the table (every hop is evaluated; for testing)
-    uint32_t launch_id;   // entries are valid only with the tag (launch_id, member + 1): the table is zeroed ONCE, at
-                          // allocation, and never reset -- neither per launch nor per member
+    uint32_t launch_id;   // hop_memo.cu / hop_wide.cu: entries are valid only with the tag (launch_id, member + 1): the table
+                          // is zeroed ONCE, at allocation, and never reset -- neither per launch nor per member
+    // hop_lanes.cu: Philox round keys (key + r * Weyl constants, r = 0..9) and the slicing of the queue's tail: blocks
+    // [0, lanes_nb_full) run all their hops as one work item, the others in lanes_ns slices of lanes_slice_hops hops
+    // (a multiple of 64), handed out slice-major; lanes_prog[block - lanes_nb_full] = slices done, lanes_ck[member] =
+    // occupation mask between slices (time and tallies are checkpointed in the output arrays)
+    uint32_t rk[20];
+    int64_t lanes_nb_full, lanes_slice_hops;
+    int lanes_ns;
+    uint32_t *lanes_prog, *lanes_ck;
 };
 
 // launchers (return cudaError_t of the launch)

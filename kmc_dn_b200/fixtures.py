@@ -24,9 +24,14 @@ class _RestrictedUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if (module, name) not in _ALLOWED:
             raise pickle.UnpicklingError(f"refusing global {module}.{name} in .kmc file")
-        if module.startswith("numpy.core"):
-            module = module.replace("numpy.core", "numpy._core")
-        mod = __import__(module, fromlist=[name])
+        # import the module as the file names it; only if this numpy does not have it, try the other spelling of the
+        # same package (numpy.core <-> numpy._core: the fixtures were written by a numpy that had `numpy.core`)
+        try:
+            mod = __import__(module, fromlist=[name])
+        except ImportError:
+            other = (module.replace("numpy._core", "numpy.core") if module.startswith("numpy._core")
+                     else module.replace("numpy.core", "numpy._core"))
+            mod = __import__(other, fromlist=[name])
         return getattr(mod, name)
 
 
