@@ -200,7 +200,8 @@ int kmcb200_probe_rates(kmcb200_layout *layout, const double *E_constant, const 
                         int energies_given, float *rates_out /*[S*S]*/);
 
 /* Micro-benchmarks of the pipes that bound the hop loop, measured on `device`:
- * what = 0 MUFU.EX2 (ex2/s), 1 FP32 FFMA (fma/s), 2 warp-instruction issue (warp-instructions/s). */
+ * what = 0 MUFU.EX2 (ex2/s), 1 FP32 FFMA (fma/s), 2 warp-instruction issue (warp-instructions/s),
+ * 3 scattered 32-byte table lookups from L2 (sectors/s: the access pattern of the thread-per-trajectory kernel's hit path). */
 double kmcb200_measure_peak(int device, int what);
 
 /* Number of kernel launches issued by this library since load (bench.py's gpu_launches). */

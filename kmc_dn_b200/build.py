@@ -48,13 +48,14 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     deps = [os.path.join(CSRC, d) for d in DEPS] + [os.path.abspath(__file__)]
+    tune = os.environ.get("KMCB200_NVCC_FLAGS", "").split()  # tuning experiments only, e.g. -DLANES_MIN_CTAS=7
     objs, jobs = [], []
     for src, extra in UNITS.items():
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + deps):
-            jobs.append([nvcc] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            jobs.append([nvcc] + ARCH + COMMON + extra + tune + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
     if jobs:  # the translation units are independent: compile them side by side
         from concurrent.futures import ThreadPoolExecutor
 

@@ -58,7 +58,7 @@ namespace kmcb200 {
 
 #define LSETB 128u  // bytes per set (2 ways x 64 B)
 #ifndef LANES_MIN_CTAS
-#define LANES_MIN_CTAS 8  // resident CTAs of 4 warps per SM the register budget is set for
+#define LANES_MIN_CTAS 7  // resident CTAs of 4 warps per SM the register budget is set for (72 registers: measured 1.60e11 hops/s on C3 against 1.26e11 with 8 CTAs / 64 registers -- spills in the hop loop -- and 1.57e11 with 6)
 #endif
 #define LANES_K 14        // events per entry
 #define LANES_RMAX 8      // runs of a warp whose parameters live in shared memory (later runs: from global memory)
@@ -464,10 +464,11 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     const int tlog = E.gtab_log;  // log2(sets per warp slot), >= 6
     const int64_t wslot = (int64_t)blockIdx.x * nwarps + warp;
     unsigned char *const wtab = E.gtab + ((size_t)wslot << tlog) * LSETB;
-    const bool use_table = !(E.lanes_flags & 1);
+    // (the table can only be switched off in the DBG instantiation: the hot loop of the production one carries no test for it)
+    const bool use_table = DBG ? !(E.lanes_flags & 1) : true;
     ctx.wtab = wtab;
     ctx.use_table = use_table;
-    const int64_t total_hops = E.prehops + E.hops, prehops = E.prehops;
+    const int total_hops = (int)(E.prehops + E.hops), prehops = (int)E.prehops;  // (the host routes runs of 2^31 hops elsewhere)
     const int64_t nblocks = (E.B + 31) >> 5;
     const int64_t nb_full = E.lanes_nb_full, nb_sl = nblocks - nb_full;
     const int ns = E.lanes_ns;
@@ -479,7 +480,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         if (lane == 0) mq = atomicAdd(E.queue, 1ULL);
         const int64_t item = (int64_t)__shfl_sync(FULL, mq, 0);
         if (item >= n_items) break;
-        int64_t blk, hA, hB;
+        int64_t blk;
+        int hA, hB;
         int s0 = 0, s1 = ns;
         if (item < nb_full) {
             blk = item;
@@ -490,8 +492,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             s0 = (int)(q / nb_sl);
             s1 = s0 + 1;
             blk = nb_full + q % nb_sl;
-            hA = (int64_t)s0 * E.lanes_slice_hops;
-            hB = (s1 == ns) ? total_hops : (int64_t)s1 * E.lanes_slice_hops;
+            hA = s0 * (int)E.lanes_slice_hops;
+            hB = (s1 == ns) ? total_hops : s1 * (int)E.lanes_slice_hops;
         }
         const bool first = s0 == 0, last = s1 == ns;
         const int64_t base = blk << 5;
@@ -589,6 +591,11 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                  : "l"(LANES_SET(mask))                                                                                \
                  : "memory")
         if (alive && use_table) LANES_FETCH(occ);
+        // (a thread without a live trajectory looks like a sector-A hit -- f0 == occ, X <= f7 -- and is skipped at `apply`)
+        if (!alive) { f0 = occ; f7 = 0xffffffffu; }
+        // (opaque to ptxas: otherwise it re-derives these from %tid and the kernel parameters inside the hop loop)
+        uint32_t a_tal_me = a_tal + lane * 4u, gm_lo = (uint32_t)gm, gm_hi = (uint32_t)(gm >> 32);
+        asm volatile("" : "+r"(a_tal_me), "+r"(gm_lo), "+r"(gm_hi));
 
         // one hop of this thread's trajectory: er -> dwell time, xr -> event
         bool stop = false;
@@ -599,14 +606,13 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         const uint32_t X = xr | 0xfffu;                                                                                \
         uint32_t code = select6(X, f2, f3, f4, f5, f6, f7);                                                            \
         uint32_t rt = f1;                                                                                              \
-        uint32_t st = 0;                                                                                               \
-        if (alive) st = (f0 != occ) ? 1u : (X > f7 ? 2u : 0u);                                                         \
+        const uint32_t st = (f0 != occ) ? 1u : (X > f7 ? 2u : 0u);                                                     \
         if (__any_sync(FULL, st != 0)) {                                                                               \
             const uint2 r = lanes_cold<PT, DBG, NR>(E, ctx, occ, xr, st, f1, f7, ri, setofs, leader);                  \
             if (st) {                                                                                                  \
                 code = r.x;                                                                                            \
                 rt = r.y;                                                                                              \
-                if (r.x >> 31) { alive = false; dead = true; }                                                         \
+                if (r.x >> 31) { alive = false; dead = true; f0 = occ; f7 = 0xffffffffu; }                             \
                 if (DBG && ((r.x >> 30) & 1u)) ++n_miss;                                                               \
             }                                                                                                          \
             if (!__any_sync(FULL, alive)) { stop = true; break; }                                                      \
@@ -617,8 +623,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             const uint32_t evt = (code >> 5) & 127u;                                                                   \
             occ ^= bit_wrap(code) | bit_clamp(evt);                                                                    \
             if (evt >= 32u) {                                                                                          \
-                const uint32_t a = a_tal + (evt & 31u) * 128u + lane * 4u;                                             \
-                sts_u(a, lds_u(a) + (evt < 64u ? 1u : 0xffffffffu));                                                   \
+                const uint32_t a = a_tal_me + (evt & 31u) * 128u;                                                      \
+                sts_u(a, lds_u(a) + 1u - ((evt >> 5) & 2u));                                                           \
             }                                                                                                          \
             t_part = fmaf(lg, __uint_as_float(rt), t_part);                                                            \
             if (DBG && E.trace && (h_) >= prehops) {                                                                   \
@@ -627,7 +633,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 if (evt < 32u) { from = site; to = (int)evt; }                                                         \
                 else if (evt < 64u) { from = site; to = N + (int)evt - 32; }                                           \
                 else { from = N + (int)evt - 64; to = site; }                                                          \
-                int32_t *tp = E.trace + (m * E.hops + ((h_) - prehops)) * 2;                                           \
+                int32_t *tp = E.trace + (m * E.hops + (int64_t)((h_) - prehops)) * 2;                                  \
                 tp[0] = from;                                                                                          \
                 tp[1] = to;                                                                                            \
             }                                                                                                          \
@@ -636,7 +642,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     } while (0)
 
         // segments: a segment never straddles a 64-hop variate block or the prehops boundary
-        for (int64_t h0 = hA; h0 < hB && !stop;) {
+        for (int h0 = hA; h0 < hB && !stop;) {
             if (h0 == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
                 t_acc = 0.0;
                 t_part = 0.0f;
@@ -645,17 +651,16 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 t_acc += (double)t_part;
                 t_part = 0.0f;
             }
-            int64_t hend = (h0 | 63) + 1;
+            int hend = (h0 | 63) + 1;
             if (hend > hB) hend = hB;
             if (h0 < prehops && hend > prehops) hend = prehops;
-            const int q0 = (int)(h0 & 63), q1 = q0 + (int)(hend - h0);
-            const uint64_t blk0 = (uint64_t)(h0 >> 6) * 32u;
+            const int q0 = h0 & 63, q1 = q0 + (hend - h0);
+            const uint32_t blk0 = (uint32_t)(h0 >> 6) * 32u;  // (< 2^30: the counter's second word stays 0)
             uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
             for (int q = q0; q < q1 && !stop; ++q) {
                 uint32_t er, xq;
                 if (!(q & 1) || q == q0) {  // (q0 odd: second half of a pair whose first hop belonged to the previous segment)
-                    const uint64_t cb = blk0 + (uint64_t)(q >> 1);
-                    r4 = philox_rk(make_uint4((uint32_t)cb, (uint32_t)(cb >> 32), (uint32_t)gm, (uint32_t)(gm >> 32)), E.rk);
+                    r4 = philox_rk(make_uint4(blk0 + (uint32_t)(q >> 1), 0u, gm_lo, gm_hi), E.rk);
                 }
                 if (q & 1) { er = r4.z; xq = r4.w; }
                 else { er = r4.x; xq = r4.y; }
@@ -703,7 +708,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
 template <int PT>
 static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     using G = LanesGeom<PT>;
-    const bool dbg = E.trace || E.misses;
+    const bool dbg = E.trace || E.misses || (E.lanes_flags & 1);  // (the table can be switched off only in the DBG instantiation)
     const int warps = 4;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     // candidates per acceptor for the K largest events of a state

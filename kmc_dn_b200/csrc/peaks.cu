@@ -3,6 +3,10 @@
 //   what = 0: MUFU.EX2 throughput (ex2.approx per second, all SMs)
 //   what = 1: FP32 FFMA throughput (fma per second)
 //   what = 2: warp-instruction issue rate (FFMA + LOP3 mix on both FP/INT pipes; warp-instructions per second)
+//   what = 3: scattered table lookups: every thread reads 32-byte sectors at independent pseudo-random places of an
+//             L2-resident 32 MiB table with 256-bit loads, 8 in flight (sectors per second) -- the access pattern of the
+//             thread-per-trajectory kernel's hit path (hop_lanes.cu: one 32-byte entry sector per hop and thread), whose
+//             hardware limit is the L1TEX data pipe: one wavefront (here = one thread's sector) per clock and SM
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -35,11 +39,59 @@ __global__ void __launch_bounds__(256) peak_kernel(float *sink, int iters) {
     if (s == 1.2345e-30f) sink[0] = s;
 }
 
-// returns operations per second (thread-level ops for 0/1, warp-instructions for 2); <0 on error
+__global__ void __launch_bounds__(256) lookup_peak_kernel(const unsigned char *table, uint32_t mask, uint32_t *sink, int iters) {
+    uint32_t x = (blockIdx.x * 256u + threadIdx.x) * 2654435761u + 12345u, acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t a[8], v[8][8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x = x * 1664525u + 1013904223u;
+            a[k] = (x >> 5) & mask;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("ld.global.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(v[k][0]), "=r"(v[k][1]), "=r"(v[k][2]), "=r"(v[k][3]), "=r"(v[k][4]), "=r"(v[k][5]), "=r"(v[k][6]), "=r"(v[k][7])
+                         : "l"(table + (size_t)a[k] * 32u));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc ^= v[k][0] ^ v[k][7];
+    }
+    if (acc == 0x12345678u) sink[0] = acc;
+}
+
+static double measure_lookup_peak(int sms, int *launches) {
+    const size_t bytes = (size_t)32 << 20;
+    unsigned char *table = nullptr;
+    uint32_t *sink = nullptr;
+    if (cudaMalloc(&table, bytes) != cudaSuccess) return -1.0;
+    if (cudaMalloc(&sink, 4) != cudaSuccess) { cudaFree(table); return -1.0; }
+    cudaMemset(table, 1, bytes);
+    const int blocks = sms * 8, threads = 256, iters = 1 << 10;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        lookup_peak_kernel<<<blocks, threads>>>(table, (uint32_t)(bytes / 32 - 1), sink, iters);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = -1.0; break; }
+        if (launches) ++*launches;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double rate = (double)blocks * threads * iters * 8.0 / (ms * 1e-3);
+        if (rep > 0 && rate > best) best = rate;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(table); cudaFree(sink);
+    return best;
+}
+
+// returns operations per second (thread-level ops for 0/1/3, warp-instructions for 2); <0 on error
 double measure_peak(int what, int *launches) {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (what == 3) return measure_lookup_peak(sms, launches);
     float *sink = nullptr;
     if (cudaMalloc(&sink, 4) != cudaSuccess) return -1.0;
     const int blocks = sms * 8, threads = 256, iters = 1 << 14;
