@@ -563,6 +563,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             for (int e = 0; e < P; ++e) sts_u(a_tal + (uint32_t)e * 128u + lane * 4u, 0u);
             if (E.occupation0 && active)
                 for (int i = 0; i < N; ++i) occ |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
+            if (DBG && E.avg_occupation && active)
+                for (int i = 0; i < N; ++i) E.avg_occupation[m * N + i] = 0.0;
         } else {
             if (lane == 0) {
                 const volatile uint32_t *pr = E.lanes_prog + (blk - nb_full);
@@ -599,10 +601,10 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
 
         // one hop of this thread's trajectory: er -> dwell time, xr -> event
         bool stop = false;
-#define LANES_HOP(er_, xr_, h_)                                                                                        \
+#define LANES_HOP(lg_, xr_, h_)                                                                                        \
     do {                                                                                                               \
         const uint32_t xr = (xr_);                                                                                     \
-        const float lg = lg2_approx(fmaf((float)(er_), 2.3283064365386963e-10f, 1.1641532182693481e-10f));            \
+        const float lg = (lg_);                                                                                        \
         const uint32_t X = xr | 0xfffu;                                                                                \
         uint32_t code = select6(X, f2, f3, f4, f5, f6, f7);                                                            \
         uint32_t rt = f1;                                                                                              \
@@ -627,15 +629,28 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 sts_u(a, lds_u(a) + 1u - ((evt >> 5) & 2u));                                                           \
             }                                                                                                          \
             t_part = fmaf(lg, __uint_as_float(rt), t_part);                                                            \
-            if (DBG && E.trace && (h_) >= prehops) {                                                                   \
+            if (DBG && (E.trace || E.traffic || E.avg_occupation) && (h_) >= prehops) {                                \
                 const int site = (int)(code & 31u);                                                                    \
                 int from, to;                                                                                          \
                 if (evt < 32u) { from = site; to = (int)evt; }                                                         \
                 else if (evt < 64u) { from = site; to = N + (int)evt - 32; }                                           \
                 else { from = N + (int)evt - 64; to = site; }                                                          \
-                int32_t *tp = E.trace + (m * E.hops + (int64_t)((h_) - prehops)) * 2;                                  \
-                tp[0] = from;                                                                                          \
-                tp[1] = to;                                                                                            \
+                if (E.trace) {                                                                                         \
+                    int32_t *tp = E.trace + (m * E.hops + (int64_t)((h_) - prehops)) * 2;                              \
+                    tp[0] = from;                                                                                      \
+                    tp[1] = to;                                                                                        \
+                }                                                                                                      \
+                if (E.traffic) { /* simulation.go:310-311: antisymmetric hop counts */                                 \
+                    double *tr = E.traffic + m * (int64_t)S * S;                                                       \
+                    tr[from * S + to] += 1.0;                                                                          \
+                    tr[to * S + from] -= 1.0;                                                                          \
+                }                                                                                                      \
+                if (E.avg_occupation) { /* simulation.go:312-316 as time stamps: a site collects t_off - t_on */      \
+                    const double now = t_acc + (double)t_part;                                                         \
+                    double *row = E.avg_occupation + m * N;                                                            \
+                    if (from < N) row[from] += now;                                                                    \
+                    if (to < N) row[to] -= now;                                                                        \
+                }                                                                                                      \
             }                                                                                                          \
             if (use_table) LANES_FETCH(occ);                                                                           \
         }                                                                                                              \
@@ -647,6 +662,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 t_acc = 0.0;
                 t_part = 0.0f;
                 for (int e = 0; e < P; ++e) sts_u(a_tal + (uint32_t)e * 128u + lane * 4u, 0u);
+                if (DBG && E.avg_occupation && active)
+                    for (int i = 0; i < N; ++i) E.avg_occupation[m * N + i] = 0.0;
             } else {
                 t_acc += (double)t_part;
                 t_part = 0.0f;
@@ -664,7 +681,14 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 }
                 if (q & 1) { er = r4.z; xq = r4.w; }
                 else { er = r4.x; xq = r4.y; }
-                LANES_HOP(er, xq, h0 + (q - q0));
+                // dwell time = lg * (-ln2 / total): lg = log2 of a uniform in (0, 1), or of exp(-e) for an injected variate
+                float lgv;
+                if (DBG && E.stream_e) {  // injected stream: e = Exp(1) variate (f64), u = uniform in [0, 1) (f32), simulation.go:297-299
+                    const int64_t ix = m * (int64_t)total_hops + (h0 + (q - q0));
+                    lgv = active ? (float)(-1.4426950408889634 * E.stream_e[ix]) : 0.0f;
+                    xq = active ? __float2uint_rz(E.stream_u[ix] * 4294967296.0f) : 0u;
+                } else lgv = lg2_approx(fmaf((float)er, 2.3283064365386963e-10f, 1.1641532182693481e-10f));
+                LANES_HOP(lgv, xq, h0 + (q - q0));
             }
             h0 = hend;
         }
@@ -680,8 +704,13 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             for (int e = 0; e < P; ++e) E.electrode_occ[m * P + e] = (int64_t)(int32_t)lds_u(a_tal + (uint32_t)e * 128u + lane * 4u);
             if (DBG && E.misses) E.misses[m] = n_miss;
             if (!last) E.lanes_ck[m] = occ;
-            else if (E.occupation_out)
-                for (int i = 0; i < N; ++i) E.occupation_out[m * N + i] = (occ >> i) & 1u;
+            else {
+                if (E.occupation_out)
+                    for (int i = 0; i < N; ++i) E.occupation_out[m * N + i] = (occ >> i) & 1u;
+                if (DBG && E.avg_occupation)  // sites still occupied collect t_end - t_on
+                    for (int i = 0; i < N; ++i)
+                        if ((occ >> i) & 1u) E.avg_occupation[m * N + i] += t_acc;
+            }
         }
         if (last && E.site_energies_out) {
             for (int t = 0; t < 32; ++t) {
@@ -708,7 +737,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
 template <int PT>
 static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
     using G = LanesGeom<PT>;
-    const bool dbg = E.trace || E.misses || (E.lanes_flags & 1);  // (the table can be switched off only in the DBG instantiation)
+    // (record outputs, injected streams and the table-off switch exist only in the DBG instantiation)
+    const bool dbg = E.trace || E.misses || (E.lanes_flags & 1) || E.traffic || E.avg_occupation || E.stream_e;
     const int warps = 4;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     // candidates per acceptor for the K largest events of a state

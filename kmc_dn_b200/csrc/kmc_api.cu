@@ -341,9 +341,9 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         //      (below that the warp-per-trajectory kernel has more parallelism to offer)
         bool lanes = false;
         {
-            const bool lanes_ok = narrow && !E.stream_e && !E.avg_occupation && !E.traffic && th < kLanesMaxHops;
+            const bool lanes_ok = narrow && th < kLanesMaxHops;
             if (a->flags & KMCB200_FLAG_LANES) {
-                if (!lanes_ok) return fail("kmcb200_run_ensemble: the thread-per-trajectory kernel needs N <= 31, fewer than 2^31 hops and has no record / injected-stream outputs");
+                if (!lanes_ok) return fail("kmcb200_run_ensemble: the thread-per-trajectory kernel needs N <= 31 and fewer than 2^31 hops");
                 lanes = true;
             } else if (!(a->flags & KMCB200_FLAG_NO_LANES) && lanes_ok) {
                 lanes = B >= kLanesAutoMinB && !(a->flags & KMCB200_FLAG_NO_MEMO);

@@ -22,6 +22,11 @@ WANT = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_elapsed.max",
     "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+    # round 2: the memory side of the table look-ups
+    "sm__cycles_active.avg", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sectors.sum",
+    "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum",
 ]
 STALLS = "smsp__average_warps_issue_stalled_"
 
@@ -47,6 +52,11 @@ def main():
                      ), reverse=True)[:8]
     for v, k in stalls:
         print(f"stall {k[len(STALLS):-len('_per_warp_active.pct')]:40s} {v:8.2f} %")
+    # cycles a warp waits per instruction it issues, by reason (their sum = cycles between two issues of a warp)
+    per_issue = sorted(((float(v[1].replace(",", "") or 0), k) for k, v in d.items()
+                        if k.startswith(STALLS) and k.endswith("_per_issue_active.ratio") and "not_issued" not in k), reverse=True)[:9]
+    for v, k in per_issue:
+        print(f"stall cycles per issued instruction: {k[len(STALLS):-len('_per_issue_active.ratio')]:28s} {v:6.2f}")
     if "smsp__inst_executed.sum" in d:
         inst = float(d["smsp__inst_executed.sum"][1].replace(",", ""))
         print(f"warp-instructions per hop: {inst / hops:.1f}")
@@ -88,7 +98,15 @@ def main():
                "smem_bank_conflict_wavefronts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
                "smem_wavefronts": num("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
                "registers_per_thread": num("launch__registers_per_thread"),
-               "achieved_occupancy_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active")}
+               "achieved_occupancy_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+               "l1tex_data_pipe_wavefront_pct": num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+               "l1_sector_hit_pct": num("l1tex__t_sector_hit_rate.pct"), "l2_sector_hit_pct": num("lts__t_sector_hit_rate.pct"),
+               "l2_throughput_pct": num("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+               "l2_sectors_per_hop": (num("lts__t_sectors.sum") or 0) / hops,
+               "sm_active_frac": (num("sm__cycles_active.avg") or 0) / (num("sm__cycles_elapsed.max") or 1)}
+        if len(sys.argv) > 7:
+            out.update({"hops_per_member": int(sys.argv[5]), "N": int(sys.argv[6]), "P": int(sys.argv[7])})
+        out["dram_bytes_per_hop"] = ((byt("dram__bytes_read.sum") or 0) + (byt("dram__bytes_write.sum") or 0)) / hops
         if members:
             out["dram_bytes_read_per_member"] = byt("dram__bytes_read.sum") / members
             out["dram_bytes_written_per_member"] = byt("dram__bytes_write.sum") / members

@@ -233,7 +233,7 @@ def test_lanes_currents_pass_reference_acceptance(fixtures_subset):
 
 
 def test_lanes_edge_cases(golden_py):
-    """hops = 0, a single member, a dead state (closed system with nothing to do), unsupported outputs are refused."""
+    """hops = 0, a single member, a dead state (closed system with nothing to do), layouts the kernel cannot take are refused."""
     c = golden_py["fx_rnd_min_max_0"]
     lay = _layout(c)
     r = lay.run(0, c["kT"], c["electrode_v"][None], E_constant=c["E_constant"][None], occupation0=c["occupation"],
@@ -242,8 +242,11 @@ def test_lanes_edge_cases(golden_py):
     np.testing.assert_array_equal(r["occupation"][0], c["occupation"])
     r = lay.run(1000, c["kT"], c["electrode_v"][None], E_constant=c["E_constant"][None], seed=3, kernel="lanes")
     assert np.isfinite(r["time"][0]) and r["time"][0] > 0
+    lay.close()
+    big = synthetic_layout(40, 4, 3)  # more than 31 acceptors: one mask word is not enough
+    lay = _layout(big)
     with pytest.raises(RuntimeError):
-        lay.run(10, c["kT"], c["electrode_v"][None], E_constant=c["E_constant"][None], record=True, kernel="lanes")
+        lay.run(10, big["kT"], big["electrode_v"][None], E_constant=big["E_constant"][None], kernel="lanes")
     lay.close()
     d = synthetic_layout(6, 0, 5)
     d["occupation"][:] = True  # full, no electrodes: no transition possible
@@ -267,12 +270,89 @@ def test_kernel_selection(golden_py):
     lay.run(50, c["kT"], np.tile(c["electrode_v"], (70000, 1)), E_constant=np.tile(c["E_constant"], (70000, 1)), seed=1,
             kernel="warp")
     assert last_kernel() == "kmc_memo_kernel"
-    lay.run(50, c["kT"], np.tile(c["electrode_v"], (70000, 1)), E_constant=np.tile(c["E_constant"], (70000, 1)), seed=1,
-            record=True)  # record outputs exist only in the warp-per-trajectory kernel
-    assert last_kernel() == "kmc_memo_kernel"
+    r = lay.run(50, c["kT"], np.tile(c["electrode_v"], (70000, 1)), E_constant=np.tile(c["E_constant"], (70000, 1)), seed=1,
+                record=True)  # a large record=True ensemble stays on the thread-per-trajectory kernel
+    assert last_kernel() == "kmc_lanes_kernel"
+    assert np.isfinite(r["avg_occupation"]).all() and (r["traffic"] == -r["traffic"].transpose(0, 2, 1)).all()
     lay.close()
     d = synthetic_layout(40, 4, 3)
     lay = _layout(d)
     lay.run(20, d["kT"], np.tile(d["electrode_v"], (70000, 1)), E_constant=np.tile(d["E_constant"], (70000, 1)), seed=1)
     assert last_kernel() == "kmc_wide_kernel"
     lay.close()
+
+
+def test_lanes_record_outputs(golden_py, fixtures_subset):
+    """record=True on the thread-per-trajectory kernel (simulation.go:309-317): traffic is the antisymmetrised histogram of
+    the traced hops, the occupied times add up to (holes x time), both are bit-identical with the table off, restart at the
+    prehops boundary, and agree with the warp-per-trajectory kernel's tallies within statistical error."""
+    for name, c in (("fx_rnd_min_max_0", golden_py["fx_rnd_min_max_0"]), ("c2_grid_N16_P8", golden_py["c2_grid_N16_P8"]),
+                    ("XOR_wide/test1", _fixture_case(fixtures_subset["XOR_wide/test1"]))):
+        N, P = c["N"], c["P"]
+        S = N + P
+        B, hops, pre = 48, 4000, 500
+        V = np.tile(c["electrode_v"], (B, 1)) + (np.arange(B) // 16)[:, None] * 0.5
+        E = np.tile(c["E_constant"], (B, 1))
+        lay = _layout(c)
+        kw = dict(E_constant=E, occupation0=c["occupation"], prehops=pre, seed=33, record=True, trace=True, want_occupation=True,
+                  kernel="lanes")
+        a = lay.run(hops, c["kT"], V, memo=True, **kw)
+        b = lay.run(hops, c["kT"], V, memo=False, **kw)
+        for k in ("traffic", "avg_occupation", "time", "trace", "electrode_occupation"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=f"{name} {k}")
+        # traffic from the trace
+        tr = np.zeros((B, S, S))
+        for m in range(B):
+            np.add.at(tr[m], (a["trace"][m, :, 0], a["trace"][m, :, 1]), 1.0)
+        np.testing.assert_array_equal(a["traffic"], tr - tr.transpose(0, 2, 1), err_msg=name)
+        # occupied time: sum over sites = integral of the number of holes; every site within [0, time]
+        ao = a["avg_occupation"]
+        assert (ao >= -1e-9 * a["time"][:, None]).all() and (ao <= a["time"][:, None] * (1 + 1e-9)).all(), name
+        # against the warp-per-trajectory kernel (other streams): mean occupation per site
+        Bs = 512
+        Vs = np.tile(c["electrode_v"], (Bs, 1)); Es = np.tile(c["E_constant"], (Bs, 1))
+        g = lay.run(6000, c["kT"], Vs, E_constant=Es, occupation0=c["occupation"], prehops=pre, seed=5, record=True, kernel="lanes")
+        w = lay.run(6000, c["kT"], Vs, E_constant=Es, occupation0=c["occupation"], prehops=pre, seed=6, record=True, kernel="warp")
+        lay.close()
+        og, ow = g["avg_occupation"] / g["time"][:, None], w["avg_occupation"] / w["time"][:, None]
+        z = np.abs(og.mean(0) - ow.mean(0)) / np.sqrt(og.var(0) / Bs + ow.var(0) / Bs + 1e-12)
+        assert (z < 5).all(), (name, z)
+        # number of holes: sum of the occupied times / time stays within [0, N] and matches between the kernels
+        assert abs(og.sum(1).mean() - ow.sum(1).mean()) < 0.05 * N, name
+        tg, tw = g["traffic"].mean(0), w["traffic"].mean(0)
+        sd = np.sqrt(g["traffic"].var(0) / Bs + w["traffic"].var(0) / Bs) + 1e-9
+        assert (np.abs(tg - tw) < 5.5 * sd + 0.02).all(), name
+
+
+def test_lanes_injected_stream(golden_py):
+    """Injected variates (simulation.go:297-299: e ~ Exp(1) for the dwell time, u ~ U[0,1) for the pick) on the thread-per-
+    trajectory kernel: bit-identical with the table off, every hop allowed, and the elapsed time is sum e_k / total rate of
+    the state before hop k (oracle rates, fp32: 1e-5)."""
+    from oracle import oracle
+    c = golden_py["fx_rnd_min_max_0"]
+    N, P = c["N"], c["P"]
+    B, hops = 6, 60
+    rng = np.random.default_rng(8)
+    e = rng.exponential(size=(B, hops)); u = rng.random((B, hops)).astype(np.float32)
+    V = np.tile(c["electrode_v"], (B, 1)); E = np.tile(c["E_constant"], (B, 1))
+    lay = _layout(c)
+    kw = dict(E_constant=E, occupation0=c["occupation"], stream_e=e, stream_u=u, trace=True, want_occupation=True, kernel="lanes")
+    a = lay.run(hops, c["kT"], V, memo=True, **kw)
+    b = lay.run(hops, c["kT"], V, memo=False, **kw)
+    lay.close()
+    np.testing.assert_array_equal(a["trace"], b["trace"])
+    np.testing.assert_array_equal(a["time"], b["time"])
+    _check_trace(c, a, c["occupation"].copy())
+    for m in range(B):
+        occ = c["occupation"].copy()
+        t = 0.0
+        for k, (f, to) in enumerate(a["trace"][m]):
+            se = site_energies_of(c)
+            _, rates = oracle.go_rates(N, P, c["nu"], c["kT"], c["I_0"], c["R"], occ, c["distances"], c["E_constant"],
+                                       c["transitions_constant"], se)
+            t += e[m, k] / rates.astype(np.float64).sum()
+            if f < N:
+                occ[f] = False
+            if to < N:
+                occ[to] = True
+        assert a["time"][m] == pytest.approx(t, rel=2e-5), (m, a["time"][m], t)
