@@ -122,8 +122,8 @@ enum {
                                      nothing is copied and the call returns after enqueueing on `stream` */
     KMCB200_FLAG_NO_MEMO = 2,     /* MODE_FAST: disable the per-warp state memoisation (results are
                                      bit-identical either way; for testing and profiling)                */
-    KMCB200_FLAG_LANES = 4,       /* MODE_FAST, N <= 31: force the thread-per-trajectory kernel (default: chosen
-                                     for ensembles of >= 65536 members; no record / injected-stream outputs) */
+    KMCB200_FLAG_LANES = 4,       /* MODE_FAST, N <= 31, fewer than 2^31 hops: force the thread-per-trajectory kernel
+                                     (default: chosen for ensembles of >= 24576 members)                     */
     KMCB200_FLAG_NO_LANES = 8     /* MODE_FAST: never use the thread-per-trajectory kernel                 */
 };
 
@@ -181,7 +181,10 @@ kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const double *di
 void kmcb200_layout_destroy(kmcb200_layout *layout);
 
 /* Runs the ensemble on the layout's device.  Returns 0 on success, non-zero on error
- * (message via kmcb200_last_error).  Host-pointer calls are synchronous. */
+ * (message via kmcb200_last_error).  Host-pointer calls are synchronous.  Calls with KMCB200_FLAG_DEVICE_PTRS
+ * return after enqueueing; ONE launch is in flight per layout: the next call on the same layout -- from any
+ * stream -- waits on the device for the previous one (work queue, workspace and state tables belong to the
+ * layout).  For concurrent launches use one layout per stream. */
 int kmcb200_run_ensemble(kmcb200_layout *layout, const kmcb200_ensemble_args *args);
 
 /* The same call spread over several GPUs of one box from ONE process (the ensemble shards
@@ -190,6 +193,15 @@ int kmcb200_run_ensemble(kmcb200_layout *layout, const kmcb200_ensemble_args *ar
  * members are cut into contiguous blocks, one host thread per device.  Host pointers only, stream must be NULL.
  * Results are identical to a single-device call (streams are numbered by global member index). */
 int kmcb200_run_ensemble_multi(kmcb200_layout *const *layouts, int n_layouts, const kmcb200_ensemble_args *args);
+
+/* Per-voltage-vector statistics of the currents on the device (the reduction the reference's consumers do
+ * on the host: voltage_search.py:160-185, validate_tests.py:80-135).  All DEVICE pointers on `device`, asynchronous on
+ * `stream`.  Members g*group .. g*group+group-1 are the repeats (seeds) of voltage vector g:
+ *   sum[g,e]   = sum over the repeats of electrode_occ[m,e] / time[m]     (kmc_dopant_networks.py:618)
+ *   sumsq[g,e] = sum of the squares,   count[g] = repeats with a finite time (count may be NULL)
+ * so that mean and variance -- on one GPU or after an all-reduce of the three arrays -- need B/group*P values. */
+int kmcb200_reduce_currents(int device, const double *time, const int64_t *electrode_occ, int64_t B, int P, int group,
+                            double *sum /*[B/group,P]*/, double *sumsq /*[B/group,P]*/, double *count /*[B/group]*/, void *stream);
 
 /* fp32 energies + dense rate matrix of ONE given state with the FAST kernel's arithmetic
  * (parity probe for the 1e-6-relative checks).  All host pointers.  site_energies_io[S]:

@@ -47,7 +47,7 @@ EXPORTS = ["wrapperSimulate", "wrapperSimulateRecord", "wrapperSimulateRecordPlu
            "parallelSimulations", "kmcb200_device_count", "kmcb200_last_error", "kmcb200_version",
            "kmcb200_set_seed", "kmcb200_layout_create", "kmcb200_layout_destroy", "kmcb200_run_ensemble",
            "kmcb200_run_ensemble_multi",
-           "kmcb200_probe_rates", "kmcb200_launch_count", "kmcb200_last_kernel", "kmcb200_sizeof_ensemble_args", "kmcb200_measure_peak"]
+           "kmcb200_probe_rates", "kmcb200_reduce_currents", "kmcb200_launch_count", "kmcb200_last_kernel", "kmcb200_sizeof_ensemble_args", "kmcb200_measure_peak"]
 
 _lib = None
 
@@ -82,6 +82,9 @@ def load():
     lib.kmcb200_probe_rates.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_void_p]
     lib.kmcb200_probe_rates.restype = C.c_int
+    lib.kmcb200_reduce_currents.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
+    lib.kmcb200_reduce_currents.restype = C.c_int
     lib.kmcb200_launch_count.restype = C.c_longlong
     lib.kmcb200_last_kernel.restype = C.c_char_p
     lib.kmcb200_measure_peak.argtypes = [C.c_int, C.c_int]

@@ -26,6 +26,7 @@ UNITS = {
     "hop_prob.cu": ["-fmad=false", "-prec-div=true", "-prec-sqrt=true"],
     "kmc_api.cu": [],
     "peaks.cu": [],
+    "reduce.cu": [],
 }
 DEPS = ["kmc_internal.cuh", "kmc_device.cuh", "memo_common.cuh", os.path.join("..", "..", "include", "kmc_b200.h")]
 

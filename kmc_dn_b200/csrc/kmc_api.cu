@@ -516,6 +516,18 @@ extern "C" int kmcb200_run_ensemble_multi(kmcb200_layout *const *layouts, int n_
     return 0;
 }
 
+extern "C" int kmcb200_reduce_currents(int device, const double *time, const int64_t *electrode_occ, int64_t B, int P, int group,
+                                       double *sum, double *sumsq, double *count, void *stream) {
+    if (!time || !electrode_occ || !sum || !sumsq || group < 1 || B < 0 || P < 1) return fail("kmcb200_reduce_currents: bad arguments");
+    if (B % group) return fail("kmcb200_reduce_currents: B must be a multiple of the group size");
+    CU(cudaSetDevice(device));
+    int launches = 0;
+    cudaError_t le = launch_reduce_currents(time, electrode_occ, B, P, group, sum, sumsq, count, (cudaStream_t)stream, &launches);
+    g_launches += launches;
+    if (le != cudaSuccess) return fail(std::string("reduce launch: ") + cudaGetErrorString(le));
+    return 0;
+}
+
 extern "C" int kmcb200_probe_rates(kmcb200_layout *lay, const double *E_constant, const double *electrode_v,
                                    double kT, const uint8_t *occupation, float *site_energies_io,
                                    int energies_given, float *rates_out) {

@@ -74,5 +74,7 @@ cudaError_t launch_probe(const LayoutDev &L, const double *E_constant, const dou
                          int *launches);
 
 double measure_peak(int what, int *launches);
+cudaError_t launch_reduce_currents(const double *time, const int64_t *eo, int64_t B, int P, int group, double *sum, double *sumsq,
+                                   double *count, cudaStream_t st, int *launches);
 
 }  // namespace kmcb200

@@ -143,6 +143,15 @@ class Layout:
         if self.lib.kmcb200_run_ensemble(self._h, C.byref(a)):
             raise RuntimeError("kmcb200_run_ensemble: " + _lib.last_error())
 
+    def reduce_currents_device(self, time, electrode_occ, group, out_sum, out_sumsq, out_count=None, cuda_stream=None):
+        """Per-voltage-vector (sum, sum of squares, count) of the currents electrode_occ / time over `group` consecutive
+        members, on the device (kmcb200_reduce_currents): the inputs are the device tensors of run_device, the outputs
+        [B/group, P], [B/group, P], [B/group] float64 device tensors -- ready for an all_reduce / a small D2H copy."""
+        B = int(time.numel()) if hasattr(time, "numel") else int(time.size)
+        if self.lib.kmcb200_reduce_currents(self.device, _ptr(time), _ptr(electrode_occ), B, self.P, int(group), _ptr(out_sum),
+                                            _ptr(out_sumsq), _ptr(out_count), cuda_stream):
+            raise RuntimeError("kmcb200_reduce_currents: " + _lib.last_error())
+
     def run_prob(self, steps, kT, electrode_v, E_constant=None, basis=None, record=False):
         """Mean-field pre-screen (probSimulate, goSimulation/probabilitySimulation.go:53-157) for B members:
         `steps` relaxation steps from occupation 0.5.  Returns time[B], occupation[B,N] (fractional),

@@ -17,6 +17,30 @@ from .electrostatics import BasisPotentials
 from .goSimulation.pythonBind import callGoSimulation
 
 
+_LAYOUTS = None  # small LRU of device layouts keyed by content: python_simulation / prehops call the loop again and again
+                 # with the same tables (kmc_dopant_networks.py:580-585) -- no cudaMalloc / upload per call
+
+
+def _cached_layout(N, P, distances, transitions_constant, nu, I_0, R, keep=8):
+    import collections
+    import hashlib
+    from .ensemble import Layout
+    global _LAYOUTS
+    if _LAYOUTS is None:
+        _LAYOUTS = collections.OrderedDict()
+    d = np.ascontiguousarray(distances, dtype=np.float64); tc = np.ascontiguousarray(transitions_constant, dtype=np.float64)
+    h = hashlib.blake2b(digest_size=16)
+    h.update(d.tobytes()); h.update(tc.tobytes())
+    key = (int(N), int(P), float(nu), float(I_0), float(R), h.digest())
+    lay = _LAYOUTS.pop(key, None)
+    if lay is None:
+        lay = Layout(N, P, d, tc, nu=nu, I_0=I_0, R=R)
+        while len(_LAYOUTS) >= keep:
+            _LAYOUTS.popitem(last=False)[1].close()
+    _LAYOUTS[key] = lay  # most recently used last
+    return lay
+
+
 def _simulate_discrete_record(N_acceptors, N_electrodes, nu, kT, I_0, R, time, occupation, distances, E_constant,
                               site_energies, transitions_constant, transitions, problist, electrode_occupation,
                               hops, record=False, prehops=0):
@@ -24,18 +48,15 @@ def _simulate_discrete_record(N_acceptors, N_electrodes, nu, kT, I_0, R, time, o
     same arguments, same 5-tuple result, fp64 numba arithmetic replayed op for op on the device
     (KMCB200_MODE_PY).  The random stream is numpy's global MT19937 -- the generator the numba loop
     draws from -- consumed as (dwell, pick) per hop, so `np.random.seed(s)` makes a run reproducible."""
-    from .ensemble import Layout, MODE_PY
+    from .ensemble import MODE_PY
     hops = int(hops); prehops = int(prehops)
     N, P = int(N_acceptors), int(N_electrodes)
     u = np.random.random_sample(2 * (hops + prehops))
-    lay = Layout(N, P, distances, transitions_constant, nu=nu, I_0=I_0, R=R)
-    try:
-        r = lay.run(hops, kT, np.asarray(site_energies, dtype=np.float64)[None, N:], prehops=prehops,
-                    E_constant=np.asarray(E_constant, dtype=np.float64)[None, :], mode=MODE_PY,
-                    occupation0=np.asarray(occupation)[None, :], stream_u64=u, want_occupation=True,
-                    want_site_energies=True, record=True)
-    finally:
-        lay.close()
+    lay = _cached_layout(N, P, distances, transitions_constant, nu, I_0, R)
+    r = lay.run(hops, kT, np.asarray(site_energies, dtype=np.float64)[None, N:], prehops=prehops,
+                E_constant=np.asarray(E_constant, dtype=np.float64)[None, :], mode=MODE_PY,
+                occupation0=np.asarray(occupation)[None, :], stream_u64=u, want_occupation=True,
+                want_site_energies=True, record=True)
     occupation[:] = r["occupation"][0]
     site_energies[:N] = r["site_energies"][0][:N]
     eo = np.asarray(electrode_occupation) + r["electrode_occupation"][0]  # the loop accumulates onto its input (:119,:123)

@@ -25,15 +25,16 @@ def calc_D(meanp, meanv, std_p, std_v):
     return 0.25 * math.log(0.25 * (var_p / var_v + var_v / var_p + 2)) + 0.25 * ((meanp - meanv) ** 2) / (var_p + var_v)
 
 
-def evaluate_fixture(d, hops, runs=5, seed=0):
-    """Returns (D[P], currents[runs,P]) for one fixture dict (as returned by load_kmc)."""
+def evaluate_fixture(d, hops, runs=5, seed=0, kernel=None):
+    """Returns (D[P], currents[runs,P]) for one fixture dict (as returned by load_kmc).  kernel: None = the library's
+    choice (5 members: warp per trajectory), "lanes" = the thread-per-trajectory kernel."""
     from .ensemble import Layout
     N, P = int(d["N"]), int(d["P"])
     lay = Layout(N, P, d["distances"], d["transitions_constant"], nu=float(d["nu"]), I_0=float(d["I_0"]), R=float(d["R"]))
     try:
         # the fixtures were produced by wrapperSimulateRecordPlus: all-empty start (generate_tests.py:51)
         r = lay.run(hops, float(d["kT"]), np.tile(d["electrodes"][:, 3], (runs, 1)),
-                    E_constant=np.tile(d["E_constant"], (runs, 1)), seed=seed)
+                    E_constant=np.tile(d["E_constant"], (runs, 1)), seed=seed, kernel=kernel)
     finally:
         lay.close()
     cur = r["current"]
@@ -58,7 +59,7 @@ def compact_fixtures(npz_path):
                               stddev_currents=z["stddev_currents"][i])
 
 
-def acceptance_over_sets(npz_path, stride_5m=1, seed0=0, stride_1m=1):
+def acceptance_over_sets(npz_path, stride_5m=1, seed0=0, stride_1m=1, kernel=None):
     """The reference's acceptance run (validate_tests.py:299-350) over its four fixture sets at the fixtures' own run
     lengths (1e6 hops, 5e6 for the *5M sets).  Returns {set: dict(fixtures, pairs, D_mean, D_median, extreme)}."""
     per = {}
@@ -67,7 +68,7 @@ def acceptance_over_sets(npz_path, stride_5m=1, seed0=0, stride_1m=1):
         big = setname.endswith("5M")
         if int(t[4:]) % (stride_5m if big else stride_1m):
             continue
-        D, _ = evaluate_fixture(d, 5_000_000 if big else 1_000_000, seed=seed0 + k)
+        D, _ = evaluate_fixture(d, 5_000_000 if big else 1_000_000, seed=seed0 + k, kernel=kernel)
         per.setdefault(setname, []).append(D)
     out = {}
     for setname, Ds in per.items():

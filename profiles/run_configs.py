@@ -108,7 +108,7 @@ def main():
         ("C1-single", workloads.c1_basic(B=1), 1.0),   # single-trajectory latency
         ("C1", workloads.c1_basic(B=4096), 1.0),
         ("C2", workloads.c2_grid4x4(seeds=64), 1.0),
-        ("C3", workloads.c3_voltage_search(n_controls=1024 if q else 16384, seeds=16, hops=10000), 1.0),
+        ("C3", workloads.c3_voltage_search(n_controls=1024 if q else 16384, seeds=16, hops=100000), 1.0),  # 1e5 hops
         ("C3-4runs", workloads.c3_voltage_search(n_controls=1, seeds=1, hops=1000000), 1.0),  # latency-bound: 4 trajectories
         ("C3-1e6", workloads.c3_voltage_search(n_controls=64 if q else 1024, seeds=16, hops=1000000), 0.01 if q else 1.0),
         ("C4", workloads.c4_temperature(n_T=64, seeds=64 if q else 1024), 0.1 if q else 1.0),

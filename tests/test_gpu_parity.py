@@ -678,6 +678,107 @@ def test_generation_fitness_in_one_launch(fixtures_subset):
         assert errs[g] == pytest.approx(error_corr(cur[g], tests))
 
 
+def test_pruned_production_currents_vs_oracle(fixtures_subset):
+    """The production kernels with a pruned transition list (simulation.go:200-215, wrapperSimulatePruned,
+    validate_tests.py:323: pairs with tc <= 1e-7 max(tc) dropped) against the CPU restatement of the Go loop run with the
+    SAME cut: two-sample z per electrode current and for the elapsed time -- on a 30-acceptor fixture (narrow kernels,
+    both of them) and on the 256-acceptor layout of examples/scaling.py (wide kernel), with and without pruning."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle
+    from kmc_dn_b200 import workloads
+    from kmc_dn_b200.ensemble import Layout
+
+    def oracle_runs(N, P, nu, kT, I_0, R, d, tc, E, V, hops, cut, n, occ0):
+        def one(k):
+            se = np.zeros(N + P); se[N:] = V
+            o = oracle.go_simulate(N, P, nu, kT, I_0, R, d, E, tc, se, hops, variant=1, occupation=occ0, use_cache=False,
+                                   cut=cut, seed=1000 + k)
+            return np.append(o["electrode_occupation"] / o["time"], o["time"])
+        with ThreadPoolExecutor(max_workers=16) as ex:  # (ctypes releases the GIL)
+            return np.array(list(ex.map(one, range(n))))
+
+    def check(tag, g, o):
+        cg = np.column_stack([g["electrode_occupation"] / g["time"][:, None], g["time"]])
+        z = np.abs(cg.mean(0) - o.mean(0)) / np.sqrt(cg.var(0) / len(cg) + o.var(0) / len(o) + 1e-300)
+        assert (z < 5).all(), (tag, z)
+
+    c = _fixture_case(fixtures_subset["rnd_min_max/test2"])
+    for cut in (0.0, 1e-7, 1e-3):
+        hops, n = 20000, 48
+        o = oracle_runs(c["N"], c["P"], c["nu"], c["kT"], c["I_0"], c["R"], c["distances"], c["transitions_constant"],
+                        c["E_constant"], c["electrode_v"], hops, cut, n, c["occupation"])
+        lay = _layout(c, prune=cut)
+        for kernel in ("warp", "lanes"):
+            g = lay.run(hops, c["kT"], np.tile(c["electrode_v"], (256, 1)), E_constant=np.tile(c["E_constant"], (256, 1)),
+                        occupation0=c["occupation"], seed=17, kernel=kernel)
+            check((cut, kernel), g, o)
+        lay.close()
+    w = workloads.c5_scaling(N=256, M=25, B=64)
+    lt = w["tables"]
+    V = w["V"][0]
+    E = lt.E_constant(V)
+    for cut in (0.0, 1e-7):
+        hops, n = 3000, 32
+        o = oracle_runs(lt.N, lt.P, lt.nu, 1.0, lt.I_0, lt.R, lt.distances, lt.transitions_constant, E, V, hops, cut, n,
+                        w["occupation0"])
+        lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R, prune_threshold=cut)
+        g = lay.run(hops, 1.0, np.tile(V, (256, 1)), E_constant=np.tile(E, (256, 1)), occupation0=w["occupation0"], seed=23)
+        lay.close()
+        check((256, cut), g, o)
+
+
+def test_device_reduction_of_currents(fixtures_subset):
+    """(sum x, sum x^2, n) per voltage vector on the device == the host reduction of the per-member currents
+    (kmc_dopant_networks.py:618; consumers voltage_search.py:160-185, validate_tests.py:80-135)."""
+    import torch
+    from kmc_dn_b200 import workloads
+    from kmc_dn_b200.ensemble import Layout
+    w = workloads.c3_voltage_search(n_controls=8, seeds=16, hops=2000)
+    lt = w["tables"]
+    B, P, g = len(w["V"]), lt.P, 16
+    dev = torch.device("cuda", 0)
+    lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R)
+    V = torch.from_numpy(w["V"]).to(dev); kT = torch.from_numpy(w["kT"]).to(dev); basis = torch.from_numpy(lt.basis).to(dev)
+    t = torch.zeros(B, dtype=torch.float64, device=dev); eo = torch.zeros((B, P), dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    lay.run_device(B, 2000, kT, V, t, eo, basis=basis, seed=3, cuda_stream=st)
+    s1 = torch.zeros((B // g, P), dtype=torch.float64, device=dev); s2 = torch.zeros_like(s1)
+    n = torch.zeros(B // g, dtype=torch.float64, device=dev)
+    lay.reduce_currents_device(t, eo, g, s1, s2, n, cuda_stream=st)
+    torch.cuda.synchronize()
+    lay.close()
+    cur = (eo.double() / t[:, None]).cpu().numpy().reshape(B // g, g, P)
+    np.testing.assert_allclose(s1.cpu().numpy(), cur.sum(1), rtol=1e-12, atol=1e-18)
+    np.testing.assert_allclose(s2.cpu().numpy(), (cur ** 2).sum(1), rtol=1e-12, atol=1e-30)
+    assert (n.cpu().numpy() == g).all()
+
+
+def test_genetic_search_runs_generations_as_single_launches(fixtures_subset):
+    """SURVEY 8f-2 as a consumer: the reference's genetic voltage search (dn_search.py:411-549) on top of the batched hop
+    loop -- every generation is ONE ensemble launch; the fitness of a generation is the reference's error function (pinned
+    to the unmodified reference by tests/golden/search_eval.npz) of the seed-averaged output currents."""
+    from kmc_dn_b200 import workloads
+    from kmc_dn_b200.ensemble import Layout, launch_count
+    from kmc_dn_b200.search_eval import error_corr, genetic_search
+    w = workloads.c3_voltage_search(n_controls=4, seeds=1, hops=1000)
+    lt = w["tables"]
+    tests = [((0, 0), False), ((0, 75), True), ((75, 0), True), ((75, 75), False)]
+    lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R)
+    seen = []
+
+    def check(g, errors, cur):
+        seen.append(g)
+        # (a candidate whose four currents have no variance has an undefined correlation: nan, as in the reference)
+        np.testing.assert_allclose(errors, [error_corr(cur[k], tests) for k in range(len(errors))], rtol=1e-12, equal_nan=True)
+    l0 = launch_count()
+    best, controls, hist = genetic_search(lay, lt.basis, tests, gen_size=16, generations=4, hops=5000, seeds=4, seed=3,
+                                          occupation0=w["occupation0"], on_generation=check)
+    assert launch_count() - l0 == 4 and seen == [0, 1, 2, 3]  # one kernel launch per generation
+    lay.close()
+    assert np.isfinite(best) and controls.shape == (5,) and np.abs(controls).max() <= 150
+    assert best == pytest.approx(min(h[0] for h in hist))
+
+
 def test_mean_field_prescreen_vs_oracle(golden_py, fixtures_subset):
     """probSimulate (probabilitySimulation.go:53-157) on the GPU vs its C restatement: time, fractional
     occupations, electrode tallies, acceptor energies, traffic and occupied time to fp64 rounding; and through the

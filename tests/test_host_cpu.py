@@ -153,6 +153,34 @@ def test_search_error_function_matches_reference_formula():
         generation_members(np.zeros((1, 4)), tests, 8)
 
 
+def test_search_error_functions_match_the_unmodified_reference():
+    """error_corr / error_diff against golden (currents -> error) pairs computed by the UNMODIFIED reference functions
+    voltage_search.evaluate_error_corr, evaluate_error_corr_parallel and evaluate_error_diff (voltage_search.py:92-185),
+    imported in the build container by oracle/make_golden_search.py: 3 logic tables x 40 candidates, corr_pow 1..3."""
+    import os
+    from kmc_dn_b200.search_eval import error_corr, error_diff
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "search_eval.npz"))
+    n = 0
+    for name in ("xor", "and", "or"):
+        tests = [(tuple(i), bool(e)) for i, e in zip(z[f"{name}_tests_inputs"], z[f"{name}_tests_expected"])]
+        for v, cp, e_seq, e_par, e_dif in zip(z[f"{name}_values"], z[f"{name}_corr_pow"], z[f"{name}_error_corr"],
+                                              z[f"{name}_error_corr_parallel"], z[f"{name}_error_diff"]):
+            assert e_seq == e_par  # the reference's two code paths agree with each other
+            assert error_corr(v, tests, corr_pow=int(cp)) == e_seq, (name, v, cp)
+            assert error_diff(v, tests) == e_dif
+            n += 1
+    assert n == 120
+
+
+def test_genetic_search_gene_coding():
+    """uint16 gene coding of voltage_search.getGenes / getDnFromGenes (voltage_search.py:214-227)."""
+    from kmc_dn_b200.search_eval import controls_of, genes_of
+    v = np.array([-150.0, -75.0, 0.0, 149.0, 150.0])
+    g = genes_of(v, 150.0)
+    assert g.dtype == np.uint16 and g[0] == 0 and g[-1] == 65535
+    np.testing.assert_allclose(controls_of(g, 150.0), v, atol=300 / 65535)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints ONE JSON line carrying the keys of
     the bench contract; it needs no GPU.  Tiny sample here -- the driver's run uses the defaults."""
