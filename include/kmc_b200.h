@@ -123,7 +123,7 @@ enum {
     KMCB200_FLAG_NO_MEMO = 2,     /* MODE_FAST: disable the per-warp state memoisation (results are
                                      bit-identical either way; for testing and profiling)                */
     KMCB200_FLAG_LANES = 4,       /* MODE_FAST, N <= 31, fewer than 2^31 hops: force the thread-per-trajectory kernel
-                                     (default: chosen for ensembles of >= 24576 members)                     */
+                                     (default: chosen for ensembles of >= 12288 members)                     */
     KMCB200_FLAG_NO_LANES = 8     /* MODE_FAST: never use the thread-per-trajectory kernel                 */
 };
 

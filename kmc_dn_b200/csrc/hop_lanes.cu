@@ -469,7 +469,8 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     ctx.wtab = wtab;
     ctx.use_table = use_table;
     const int total_hops = (int)(E.prehops + E.hops), prehops = (int)E.prehops;  // (the host routes runs of 2^31 hops elsewhere)
-    const int64_t nblocks = (E.B + 31) >> 5;
+    const int mlog = E.lanes_mpb_log, mpb = 1 << mlog;  // members per block: 32, or 16 / 8 for ensembles that would leave warp slots empty
+    const int64_t nblocks = (E.B + mpb - 1) >> mlog;
     const int64_t nb_full = E.lanes_nb_full, nb_sl = nblocks - nb_full;
     const int ns = E.lanes_ns;
     const int64_t n_items = nb_full + nb_sl * ns;
@@ -496,9 +497,9 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             hB = (s1 == ns) ? total_hops : s1 * (int)E.lanes_slice_hops;
         }
         const bool first = s0 == 0, last = s1 == ns;
-        const int64_t base = blk << 5;
+        const int64_t base = blk << mlog;
         const int64_t m = base + lane;
-        const bool active = m < E.B;
+        const bool active = lane < mpb && m < E.B;
         const int64_t mc = active ? m : E.B - 1;
         ctx.base = base;
 
@@ -715,7 +716,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         if (last && E.site_energies_out) {
             for (int t = 0; t < 32; ++t) {
                 const int64_t mt = base + t;
-                if (mt >= E.B) break;
+                if (t >= mpb || mt >= E.B) break;
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 double E64;
                 float ve_t, nbt;
@@ -754,10 +755,12 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
-    const int64_t want = (E.B + warps * 32 - 1) / (warps * 32);
+    const int64_t mpb = (int64_t)1 << E.lanes_mpb_log;
+    const int64_t want = (E.B + warps * mpb - 1) / (warps * mpb);
     const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
     if (plan_only) {
         plan_only->warp_slots = (int64_t)grid * warps;
+        plan_only->max_slots = (int64_t)sms * per_sm * warps;
         return cudaSuccess;
     }
     kern<<<grid, warps * 32, smem, st>>>(L, E);
@@ -769,10 +772,10 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
 // E.gtab = warp_slots * 2^E.gtab_log sets of 128 bytes and the slicing of the queue's tail from it.
 cudaError_t launch_lanes(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan) {
     if (E.B <= 0) {
-        if (plan) plan->warp_slots = 0;
+        if (plan) { plan->warp_slots = 0; plan->max_slots = 0; }
         return cudaSuccess;
     }
-    if (L.N > 31 || L.P > 32 || L.pitchf != 33) return cudaErrorInvalidValue;
+    if (L.N > 31 || L.P > 32 || L.pitchf != 33 || E.lanes_mpb_log < 3 || E.lanes_mpb_log > 5) return cudaErrorInvalidValue;
     if (!plan && !(E.lanes_flags & 1) && (!E.gtab || E.gtab_log < 6)) return cudaErrorInvalidValue;
     if (L.P == 8) return launch_lanes_t<8>(L, E, st, launches, plan);
     if (L.P == 2) return launch_lanes_t<2>(L, E, st, launches, plan);

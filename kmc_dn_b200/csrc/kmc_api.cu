@@ -207,7 +207,7 @@ size_t a256(size_t b) { return (b + 255) & ~size_t(255); }
 
 // MODE_FAST, N <= 31: ensembles of at least this many members run on the thread-per-trajectory kernel (hop_lanes.cu);
 // its electrode tallies are 32-bit, so runs of 2^31 hops or more stay on the warp-per-trajectory kernels
-static const int64_t kLanesAutoMinB = 24576;
+static const int64_t kLanesAutoMinB = 12288;
 static const int64_t kLanesMaxHops = (int64_t)1 << 31;
 
 static int validate(const kmcb200_layout *lay, const kmcb200_ensemble_args *a) {
@@ -356,10 +356,24 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                 E.rk[2 * r] = (uint32_t)a->seed + (uint32_t)r * 0x9E3779B9u;
                 E.rk[2 * r + 1] = (uint32_t)(a->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
             }
-            MemoPlan plan{0};
+            MemoPlan plan{0, 0};
+            E.lanes_mpb_log = 5;
             le = launch_lanes(D, E, st, nullptr, &plan);
             if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-            const int64_t W = plan.warp_slots, nblocks = (B + 31) / 32;
+            // members per warp: 32; 16 or 8 when full warps would leave more than half of the device's warp slots empty (a warp's
+            // hop costs the same whatever the number of live lanes, so spreading the members costs nothing and halves what a
+            // warp has to evaluate; below 16 the seeds of a voltage vector no longer share one table)
+            // (measured on C3 x 1e5 hops, profiles/r02/exp4_members_per_warp.jsonl: 65 536 members 6.6e10 / 7.7e10 / 5.2e10 hops/s
+            //  with 32 / 16 / 8 members per warp, 32 768: 3.4e10 / 5.0e10 / 4.6e10, 16 384: 1.8e10 / 2.9e10 / 3.2e10)
+            if (2 * ((B + 31) / 32) <= plan.max_slots) E.lanes_mpb_log = 4;
+            if (3 * ((B + 15) / 16) <= plan.max_slots) E.lanes_mpb_log = 3;
+            if (const char *ev = getenv("KMCB200_LANES_MPB_LOG")) E.lanes_mpb_log = std::max(3, std::min(5, atoi(ev)));
+            if (E.lanes_mpb_log != 5) {
+                le = launch_lanes(D, E, st, nullptr, &plan);
+                if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
+            }
+            const int64_t mpb = (int64_t)1 << E.lanes_mpb_log;
+            const int64_t W = plan.warp_slots, nblocks = (B + mpb - 1) / mpb;
             // ---- the tail of the queue in slices of hops (hop_lanes.cu, "Scheduling"): with more than one round of blocks
             //      per warp slot the launch would otherwise end on a few warps finishing whole blocks
             E.lanes_nb_full = nblocks; E.lanes_ns = 1; E.lanes_slice_hops = th; E.lanes_prog = nullptr; E.lanes_ck = nullptr;
@@ -419,7 +433,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         if (logk < 0 || glog < 1 || glog > 12) glog = 0;
         E.gtab = nullptr; E.gtab_log = 0;
         if (glog > 0) {  // second-level cache table: one region per persistent warp slot, kept with the layout
-            MemoPlan plan{0};
+            MemoPlan plan{0, 0};
             le = narrow ? launch_memo(D, E, logk, st, nullptr, &plan) : launch_wide(D, E, logk, st, nullptr, &plan);
             if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
             const size_t entry = narrow ? 288 : 448;

@@ -54,12 +54,13 @@ struct EnsembleDev {
     uint32_t rk[20];
     int64_t lanes_nb_full, lanes_slice_hops;
     int lanes_ns;
+    int lanes_mpb_log;   // log2(members per block = per warp): 5, or 4 / 3 when the ensemble would otherwise leave warp slots empty
     uint32_t *lanes_prog, *lanes_ck;
 };
 
 // launchers (return cudaError_t of the launch)
 cudaError_t launch_fast(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
-struct MemoPlan { int64_t warp_slots; };
+struct MemoPlan { int64_t warp_slots; int64_t max_slots; };  // (max_slots: hop_lanes.cu, warp slots of a full device)
 cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
                         MemoPlan *plan_only = nullptr);
 cudaError_t launch_wide(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
