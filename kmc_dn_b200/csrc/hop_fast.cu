@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 
     if (!GT) {
         float2 *stage = reinterpret_cast<float2 *>(smem_raw);
-        for (int idx = tid; idx < S * PITCH; idx += blockDim.x) stage[idx] = L.tblf[idx];
+        for (int i0 = 0; i0 < S * PITCH; i0 += blockDim.x)  // (thread-independent trip counts: see the staging loop of hop_lanes.cu)
+            if (i0 + tid < S * PITCH) stage[i0 + tid] = L.tblf[i0 + tid];
     }
     __syncthreads();
 
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 
     // ---- member parameters
     const float kT = (float)E.kT[m];
-    const float nb = -1.4426950408889634f / kT;
+    const float nb = kT;  // (the Boltzmann factor takes kT itself: kmc_device.cuh boltz)
     float se_reg[PT > 0 ? PT : 1];
     if (lane < P) mir[32 * AS + lane] = (float)E.electrode_v[m * P + lane];
     __syncwarp();
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
             s_true[k] = (float)eps64[k];
             mir[lane + 32 * k] = s_true[k];
             src[k] = o ? s_true[k] : -BIGS;         // only occupied acceptors emit to acceptors
-            nbs[k] = o ? nb : -nb;                  // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
+            nbs[k] = o ? 1.0f : -1.0f;              // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
             erow[k] = reinterpret_cast<const float *>(tbl + N * PITCH + lane + 32 * k) + (o ? 0 : 1);
         }
         __syncwarp();
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 #pragma unroll
                 for (int k = 0; k < AS; ++k) {
                     const float t = (se_reg[e] - s_true[k]) * nbs[k];
-                    rsE[k] = fmaf(erow[k][e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rsE[k]);
+                    rsE[k] = fmaf(erow[k][e * 2 * PITCH], boltz(t, nb), rsE[k]);
                 }
             }
         } else {
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
 #pragma unroll
                 for (int k = 0; k < AS; ++k) {
                     const float t = (se - s_true[k]) * nbs[k];
-                    rsE[k] = fmaf(erow[k][e * 2 * PITCH], ex2_approx(fminf(t, 0.0f)), rsE[k]);
+                    rsE[k] = fmaf(erow[k][e * 2 * PITCH], boltz(t, nb), rsE[k]);
                 }
             }
         }
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
             }
             if (to < 0) {  // electrode targets: istar -> e   (or acceptor group empty / exhausted)
                 float rr = 0.0f;
-                if (lane < P) rr = ecol[0] * ex2_approx(fminf((mir[32 * AS + lane] - s_star) * nb, 0.0f));
+                if (lane < P) rr = ecol[0] * boltz(mir[32 * AS + lane] - s_star, nb);
                 const int e = pick_in_group(rr, tryA ? BIGS : rf - rsA_star, lane);
                 if (e >= 0) to = N + e;
             }
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(256) kmc_fast_kernel(const LayoutDev L, const 
         } else {  // empty acceptor: events e -> istar
             to = istar;
             float rr = 0.0f;
-            if (lane < P) rr = ecol[1] * ex2_approx(fminf((s_star - mir[32 * AS + lane]) * nb, 0.0f));
+            if (lane < P) rr = ecol[1] * boltz(s_star - mir[32 * AS + lane], nb);
             const int e = pick_in_group(rr, rf, lane);
             if (e < 0) {
                 dead = true;

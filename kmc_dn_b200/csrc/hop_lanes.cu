@@ -68,7 +68,7 @@ template <int PT>
 struct LanesGeom {
     static constexpr int PV = PT > 0 ? PT : 32;             // electrode slots per trajectory
     static constexpr int MIRB = 256;                        // mirror: acceptor energies (128 B) | electrode energies (128 B)
-    static constexpr int RUNB = 128 + 4 * PV + 16;          // per run: E_constant row (f32 x 32) | electrode energies | -log2e/kT
+    static constexpr int RUNB = 128 + 4 * PV + 16;          // per run: E_constant row (f32 x 32) | electrode energies | kT
     static constexpr int TALB = PV * 32 * 4;                // electrode tallies [electrode][trajectory]
     static constexpr int WARP_BYTES = MIRB + LANES_RMAX * RUNB + TALB;
 };
@@ -131,16 +131,16 @@ struct LaneCtx {
 };
 
 // parameters of run r (leader = member base + ld): E_constant of acceptor `lane` (narrowed to float32,
-// simulationWrapper.go:50-56), energy of electrode `lane`, -log2(e)/kT
+// simulationWrapper.go:50-56), energy of electrode `lane`, kT (narrowed)
 template <int PT>
-__device__ __forceinline__ void run_params(const EnsembleDev &E, const LaneCtx &c, int r, int ld, double &E64, float &ve_mine, float &nbt) {
+__device__ __forceinline__ void run_params(const EnsembleDev &E, const LaneCtx &c, int r, int ld, double &E64, float &ve_mine, float &kTt) {
     using G = LanesGeom<PT>;
     const int lane = c.lane, N = c.N, P = c.P;
     if (r < LANES_RMAX) {
         const uint32_t a = c.a_run + (uint32_t)r * G::RUNB;
         E64 = (double)lds_f(a + lane * 4);
         ve_mine = (lane < P) ? lds_f(a + 128 + lane * 4) : 0.0f;
-        nbt = lds_f(a + 128 + 4 * G::PV);
+        kTt = lds_f(a + 128 + 4 * G::PV);
     } else {
         const int64_t mt = c.base + ld;
         double e64 = 0.0;
@@ -153,7 +153,7 @@ __device__ __forceinline__ void run_params(const EnsembleDev &E, const LaneCtx &
         }
         E64 = (double)(float)e64;
         ve_mine = (lane < P) ? (float)E.electrode_v[mt * P + lane] : 0.0f;
-        nbt = -1.4426950408889634f / (float)E.kT[mt];
+        kTt = (float)E.kT[mt];
     }
 }
 
@@ -171,14 +171,14 @@ struct Eval {
 
 // Evaluate state occu of a run: sweep, total, the K largest events, their quantised lengths.
 template <int PT, int NR>
-__device__ __forceinline__ bool evaluate_state(const LaneCtx &c, uint32_t occu, double E64, float ve_mine, float nbt, Eval<NR> &ev) {
+__device__ __forceinline__ bool evaluate_state(const LaneCtx &c, uint32_t occu, double E64, float ve_mine, float kTt, Eval<NR> &ev) {
     const int lane = c.lane, N = c.N, P = c.P;
     __syncwarp();
     if (lane < P) sts_f(c.a_mir + 128 + lane * 4, ve_mine);
     float rest;
     float tk[NR];
     int pk[NR];
-    sweep_state<PT, NR>(occu, c.accm, E64, lane, N, P, nbt, c.a_row_me, c.a_mir, c.a_elF, c.a_elR, ev.e_me, tk, pk, rest);
+    sweep_state<PT, NR>(occu, c.accm, E64, lane, N, P, kTt, c.a_row_me, c.a_mir, c.a_elF, c.a_elR, ev.e_me, tk, pk, rest);
     float R = rest;
 #pragma unroll
     for (int r = NR - 1; r >= 0; --r) R += tk[r];
@@ -241,7 +241,7 @@ __device__ __forceinline__ bool evaluate_state(const LaneCtx &c, uint32_t occu, 
 // events taken off (x >= F13 << 12).  A pure function of the state and x; warp-cooperative (lane = acceptor / target /
 // electrode); returns the event code (acceptor | event << 5), warp-uniform.
 template <int NR>
-__device__ __noinline__ uint32_t tail_pick(const LaneCtx &c, const Eval<NR> &ev, uint32_t occu, float nbt, float ve_mine, uint32_t x) {
+__device__ __noinline__ uint32_t tail_pick(const LaneCtx &c, const Eval<NR> &ev, uint32_t occu, float kTt, float ve_mine, uint32_t x) {
     const int lane = c.lane, N = c.N, P = c.P;
     const double unit = ev.total * 9.5367431640625e-07;  // total / 2^20
     const double u = ((double)(x - (ev.F13 << 12)) + 0.5) * 2.3283064365386963e-10 * ev.total;
@@ -290,7 +290,7 @@ __device__ __noinline__ uint32_t tail_pick(const LaneCtx &c, const Eval<NR> &ev,
             float rr = 0.0f;
             if ((emp >> lane) & 1u) {
                 const float2 v = lds_f2(c.a_col_me + istar * 8);
-                rr = fmaxf(ma(v.x, v.y, ev.e_me, e_star, nbt) - offA, 0.0f);
+                rr = fmaxf(ma(v.x, v.y, ev.e_me, e_star, kTt) - offA, 0.0f);
             }
             const uint32_t nz = __ballot_sync(FULL, rr > 0.0f);
             if (nz) {
@@ -305,7 +305,7 @@ __device__ __noinline__ uint32_t tail_pick(const LaneCtx &c, const Eval<NR> &ev,
         }
         if (to < 0) {  // electrode targets: istar -> electrode `lane`
             float rr = 0.0f;
-            if (lane < P) rr = fmaxf(lds_f(c.a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nbt, 0.0f)) - offE, 0.0f);
+            if (lane < P) rr = fmaxf(lds_f(c.a_elF_e + istar * 4) * boltz(ve_mine - e_star, kTt) - offE, 0.0f);
             const int e = pick_group<5>(rr, rf - sA);
             to = (e >= 0) ? N + e : lastA;
         }
@@ -313,7 +313,7 @@ __device__ __noinline__ uint32_t tail_pick(const LaneCtx &c, const Eval<NR> &ev,
     } else {  // empty acceptor: events electrode `lane` -> istar
         to = istar;
         float rr = 0.0f;
-        if (lane < P) rr = fmaxf(lds_f(c.a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nbt, 0.0f)) - offE, 0.0f);
+        if (lane < P) rr = fmaxf(lds_f(c.a_elR_e + istar * 4) * boltz(e_star - ve_mine, kTt) - offE, 0.0f);
         from = pick_group<5>(rr, rf);
         if (from < 0) return fallback;
         from += N;
@@ -375,10 +375,10 @@ __device__ __forceinline__ uint2 lanes_cold(const EnsembleDev &E, const LaneCtx 
         const uint32_t occu = __shfl_sync(FULL, occ, t);
         const int r = (int)__shfl_sync(FULL, ri, t);
         double E64;
-        float ve_mine, nbt;
-        run_params<PT>(E, c, r, __shfl_sync(FULL, leader, t), E64, ve_mine, nbt);
+        float ve_mine, kTt;
+        run_params<PT>(E, c, r, __shfl_sync(FULL, leader, t), E64, ve_mine, kTt);
         Eval<NR> ev;
-        const bool ok = evaluate_state<PT, NR>(c, occu, E64, ve_mine, nbt, ev);
+        const bool ok = evaluate_state<PT, NR>(c, occu, E64, ve_mine, kTt, ev);
         // threads of this run that wait on this very state (t among them) are all served by this evaluation
         const uint32_t same = __ballot_sync(FULL, ((need >> lane) & 1u) && occ == occu && ri == (uint32_t)r);
         need &= ~same;
@@ -409,7 +409,7 @@ __device__ __forceinline__ uint2 lanes_cold(const EnsembleDev &E, const LaneCtx 
             const int k = __ffs(bb) - 1;
             uint32_t c2;
             if (k < LANES_K) c2 = __shfl_sync(FULL, ev.word, k) & 4095u;
-            else c2 = tail_pick<NR>(c, ev, occu, nbt, ve_mine, x2);
+            else c2 = tail_pick<NR>(c, ev, occu, kTt, ve_mine, x2);
             if (lane == t2) {
                 code = c2;
                 rt = __float_as_uint(ev.rtp);
@@ -434,13 +434,23 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         float2 *acc = reinterpret_cast<float2 *>(smem_raw);
         float *elF = reinterpret_cast<float *>(smem_raw + (size_t)N * ROWB);
         float *elR = elF + P * 33;
-        for (int idx = tid; idx < N * 33; idx += blockDim.x) acc[idx] = L.tblf[idx];
-        for (int idx = tid; idx < P * 33; idx += blockDim.x) {
-            const float2 v = L.tblf[N * 33 + idx];
-            elF[idx] = v.x;
-            elR[idx] = v.y;
+        // (trip counts that do not depend on the thread, and a __syncwarp() behind: with `idx = tid; idx < P * 33` ptxas 12.9
+        // left the warp holding the last elements diverged up to the barrier and ran warp-uniform instructions of the code
+        // below once per group, read-modify-write ones included -- compute-sanitizer: shared stores far out of bounds)
+        for (int i0 = 0; i0 < N * 33; i0 += blockDim.x) {
+            const int idx = i0 + tid;
+            if (idx < N * 33) acc[idx] = L.tblf[idx];
+        }
+        for (int i0 = 0; i0 < P * 33; i0 += blockDim.x) {
+            const int idx = i0 + tid;
+            if (idx < P * 33) {
+                const float2 v = L.tblf[N * 33 + idx];
+                elF[idx] = v.x;
+                elR[idx] = v.y;
+            }
         }
     }
+    __syncwarp();
     __syncthreads();
 
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -469,44 +479,78 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     ctx.wtab = wtab;
     ctx.use_table = use_table;
     const int total_hops = (int)(E.prehops + E.hops), prehops = (int)E.prehops;  // (the host routes runs of 2^31 hops elsewhere)
-    const int mlog = E.lanes_mpb_log, mpb = 1 << mlog;  // members per block: 32, or 16 / 8 for ensembles that would leave warp slots empty
-    const int64_t nblocks = (E.B + mpb - 1) >> mlog;
-    const int64_t nb_full = E.lanes_nb_full, nb_sl = nblocks - nb_full;
+    const int64_t nblocks = (E.B + 31) >> 5;
     const int ns = E.lanes_ns;
+    // halves: an ensemble that would leave more than half of the device's warp slots empty gives every block of 32 members
+    // TWO warps; if a run of identical members starts at member 16 (two runs of 16 seeds: nothing is shared across the
+    // halves), they run 16 members each -- a warp's hop costs the same whatever the number of live lanes --, otherwise
+    // the first one runs the whole block and the second one returns (a run of 32 keeps ONE table).
+    const int hl = E.lanes_halves != 0;
+    const bool halves = hl != 0;
+    const int64_t nunits = nblocks << hl;
+    const int64_t nb_full = E.lanes_nb_full, nb_sl = nunits - nb_full;
     const int64_t n_items = nb_full + nb_sl * ns;
 
     // ---- persistent: every warp pulls work items from the global queue
+    //      (halves: every unit has a warp slot of its own -- the host checks it --, so a warp's ONE item is its slot number.
+    //      Where no block splits, the live units are then the first halves in the first CTAs, which the hardware spreads evenly
+    //      over the SMs; taken from a queue by 4096 warps arriving together, the live warps per SM came out binomial.)
+    if (halves) {
+        if (wslot >= nunits) return;
+        if (wslot >= nblocks) {  // a second half lives only if a run starts at member 16 of its block
+            const int64_t m16 = ((wslot - nblocks) << 5) + 16;
+            if (m16 >= E.B) return;
+            bool same = __double_as_longlong(E.kT[m16]) == __double_as_longlong(E.kT[m16 - 1]);
+            for (int p = lane; p < P; p += 32)
+                same = same && __double_as_longlong(E.electrode_v[m16 * P + p]) == __double_as_longlong(E.electrode_v[(m16 - 1) * P + p]);
+            if (E.E_constant)
+                for (int i = lane; i < N; i += 32)
+                    same = same && __double_as_longlong(E.E_constant[m16 * N + i]) == __double_as_longlong(E.E_constant[(m16 - 1) * N + i]);
+            if (__all_sync(FULL, same)) return;
+        }
+    }
+    bool own_item = halves;
     for (;;) {
-        unsigned long long mq = 0;
-        if (lane == 0) mq = atomicAdd(E.queue, 1ULL);
-        const int64_t item = (int64_t)__shfl_sync(FULL, mq, 0);
+        int64_t item;
+        if (own_item) {
+            item = wslot;
+            own_item = false;
+        } else {
+            if (halves) break;
+            unsigned long long mq = 0;
+            if (lane == 0) mq = atomicAdd(E.queue, 1ULL);
+            item = (int64_t)__shfl_sync(FULL, mq, 0);
+        }
         if (item >= n_items) break;
-        int64_t blk;
+        int64_t unit;
         int hA, hB;
         int s0 = 0, s1 = ns;
         if (item < nb_full) {
-            blk = item;
+            unit = item;
             hA = 0;
             hB = total_hops;
         } else {
             const int64_t q = item - nb_full;
             s0 = (int)(q / nb_sl);
             s1 = s0 + 1;
-            blk = nb_full + q % nb_sl;
+            unit = nb_full + q % nb_sl;
             hA = s0 * (int)E.lanes_slice_hops;
             hB = (s1 == ns) ? total_hops : s1 * (int)E.lanes_slice_hops;
         }
+        // (first halves first, see the queue above)
+        const int half = (int)(unit >= nblocks);
+        const int64_t blk = unit - (half ? nblocks : 0);
         const bool first = s0 == 0, last = s1 == ns;
-        const int64_t base = blk << mlog;
+        const int64_t base = blk << 5;
         const int64_t m = base + lane;
-        const bool active = lane < mpb && m < E.B;
-        const int64_t mc = active ? m : E.B - 1;
+        const bool present = m < E.B;
+        const int64_t mc = present ? m : E.B - 1;
         ctx.base = base;
 
         // ---- runs of identical members: bit t of sp = member t has exactly the parameters of member t-1
         uint32_t sp;
         {
-            bool eq = lane > 0 && active;
+            bool eq = lane > 0 && present;
             if (eq) {
                 eq = __double_as_longlong(E.kT[mc]) == __double_as_longlong(E.kT[mc - 1]);
                 for (int p = 0; p < P && eq; ++p)
@@ -515,10 +559,16 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                     for (int i = 0; i < N && eq; ++i)
                         eq = __double_as_longlong(E.E_constant[mc * N + i]) == __double_as_longlong(E.E_constant[(mc - 1) * N + i]);
             }
-            sp = __ballot_sync(FULL, eq || (!active && lane > 0));
+            sp = __ballot_sync(FULL, eq || (!present && lane > 0));
         }
-        const uint32_t lead_mask = ~sp;  // bit l = member l starts a run (bit 0 always does)
-        const int leader = 31 - __clz(lead_mask & (0xffffffffu >> (31 - lane)));
+        // bit l = member l starts a run (bit 0 always does); a warp that runs one half of a split block sees the runs of its
+        // half only (they share the whole of its table), and its idle lanes count as members of one of them
+        const bool split = halves && ((~sp >> 16) & 1u);
+        // (a second half whose block does not split never gets here: the taker of the first half runs the whole block)
+        const uint32_t lead_mask = split ? (~sp & (half ? 0xffff0000u : 0x0000ffffu)) : ~sp;
+        const bool active = present && (!split || (lane >> 4) == half);
+        const int lane_r = (split && (lane >> 4) != half) ? (half ? 16 : 15) : lane;
+        const int leader = 31 - __clz(lead_mask & (0xffffffffu >> (31 - lane_r)));
         const int nruns = __popc(lead_mask);
         const int slog = tlog - (nruns > 1 ? 32 - __clz(nruns - 1) : 0);  // log2(sets per run) >= 1
         const int hshift = 32 - slog;
@@ -549,7 +599,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 }
                 sts_f(a + lane * 4, ef);
                 if (lane < P) sts_f(a + 128 + lane * 4, (float)E.electrode_v[mt * P + lane]);
-                if (lane == 0) sts_f(a + 128 + 4 * PV, -1.4426950408889634f / (float)E.kT[mt]);
+                if (lane == 0) sts_f(a + 128 + 4 * PV, (float)E.kT[mt]);
             }
         }
         if (use_table)
@@ -568,7 +618,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 for (int i = 0; i < N; ++i) E.avg_occupation[m * N + i] = 0.0;
         } else {
             if (lane == 0) {
-                const volatile uint32_t *pr = E.lanes_prog + (blk - nb_full);
+                const volatile uint32_t *pr = E.lanes_prog + (unit - nb_full);
                 while (*pr < (uint32_t)s0) __nanosleep(200);
             }
             __syncwarp();
@@ -716,11 +766,12 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         if (last && E.site_energies_out) {
             for (int t = 0; t < 32; ++t) {
                 const int64_t mt = base + t;
-                if (t >= mpb || mt >= E.B) break;
+                if (mt >= E.B) break;
+                if (split && (t >> 4) != half) continue;
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 double E64;
-                float ve_t, nbt;
-                run_params<PT>(E, ctx, (int)__shfl_sync(FULL, ri, t), __shfl_sync(FULL, leader, t), E64, ve_t, nbt);
+                float ve_t, kTt;
+                run_params<PT>(E, ctx, (int)__shfl_sync(FULL, ri, t), __shfl_sync(FULL, leader, t), E64, ve_t, kTt);
                 if (lane < N) E.site_energies_out[mt * S + lane] = energy_of(occu, ctx.accm, E64, ctx.a_row_me);
                 if (lane < P) E.site_energies_out[mt * S + N + lane] = (double)ve_t;
             }
@@ -728,7 +779,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         if (!last) {
             __threadfence();
             __syncwarp();
-            if (lane == 0) atomicExch(E.lanes_prog + (blk - nb_full), (uint32_t)s1);
+            if (lane == 0) atomicExch(E.lanes_prog + (unit - nb_full), (uint32_t)s1);
         }
         __syncwarp();
 #undef LANES_SET
@@ -755,8 +806,8 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
     if (err != cudaSuccess) return err;
     if (per_sm < 1) per_sm = 1;
-    const int64_t mpb = (int64_t)1 << E.lanes_mpb_log;
-    const int64_t want = (E.B + warps * mpb - 1) / (warps * mpb);
+    const int64_t want = ((E.lanes_halves ? 2 : 1) * ((E.B + 31) / 32) + warps - 1) / warps;
+    if (E.lanes_halves && want > (int64_t)sms * per_sm) return cudaErrorInvalidValue;  // (halves: one warp slot per unit, no queue)
     const unsigned grid = (unsigned)(want < (int64_t)sms * per_sm ? want : (int64_t)sms * per_sm);
     if (plan_only) {
         plan_only->warp_slots = (int64_t)grid * warps;
@@ -775,7 +826,7 @@ cudaError_t launch_lanes(const LayoutDev &L, const EnsembleDev &E, cudaStream_t 
         if (plan) { plan->warp_slots = 0; plan->max_slots = 0; }
         return cudaSuccess;
     }
-    if (L.N > 31 || L.P > 32 || L.pitchf != 33 || E.lanes_mpb_log < 3 || E.lanes_mpb_log > 5) return cudaErrorInvalidValue;
+    if (L.N > 31 || L.P > 32 || L.pitchf != 33) return cudaErrorInvalidValue;
     if (!plan && !(E.lanes_flags & 1) && (!E.gtab || E.gtab_log < 6)) return cudaErrorInvalidValue;
     if (L.P == 8) return launch_lanes_t<8>(L, E, st, launches, plan);
     if (L.P == 2) return launch_lanes_t<2>(L, E, st, launches, plan);

@@ -115,13 +115,21 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
         float2 *acc = reinterpret_cast<float2 *>(smem_raw);
         float *elF = reinterpret_cast<float *>(smem_raw + (size_t)N * ROWB);
         float *elR = elF + P * 33;
-        for (int idx = tid; idx < N * 33; idx += blockDim.x) acc[idx] = L.tblf[idx];
-        for (int idx = tid; idx < P * 33; idx += blockDim.x) {
-            const float2 v = L.tblf[N * 33 + idx];
-            elF[idx] = v.x;
-            elR[idx] = v.y;
+        // (thread-independent trip counts: see the staging loop of hop_lanes.cu)
+        for (int i0 = 0; i0 < N * 33; i0 += blockDim.x) {
+            const int idx = i0 + tid;
+            if (idx < N * 33) acc[idx] = L.tblf[idx];
+        }
+        for (int i0 = 0; i0 < P * 33; i0 += blockDim.x) {
+            const int idx = i0 + tid;
+            if (idx < P * 33) {
+                const float2 v = L.tblf[N * 33 + idx];
+                elF[idx] = v.x;
+                elR[idx] = v.y;
+            }
         }
     }
+    __syncwarp();
     __syncthreads();
 
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
         const int64_t m = (int64_t)__shfl_sync(FULL, mq, 0);
         if (m >= E.B) break;
     // ---- member parameters
-    const float nb = -1.4426950408889634f / (float)E.kT[m];
+    const float nb = (float)E.kT[m];  // kT, narrowed as the cgo wrappers do (simulationWrapper.go:92)
     const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;  // electrode `lane`
     sts_f(a_mir + 128 + lane * 4, ve_mine);
     __syncwarp();
@@ -451,7 +459,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                             if (to < 0) {  // electrode targets: istar -> electrode `lane`
                                 float rr = 0.0f;
                                 if (lane < P && keepE)
-                                    rr = lds_f(a_elF_e + istar * 4) * ex2_approx(fminf((ve_mine - e_star) * nb, 0.0f));
+                                    rr = lds_f(a_elF_e + istar * 4) * boltz(ve_mine - e_star, nb);
                                 const int e = pick_group<5>(rr, rf - sA);
                                 to = (e >= 0) ? N + e : lastA;
                             }
@@ -460,7 +468,7 @@ __global__ void __launch_bounds__(256, 4) kmc_memo_kernel(const LayoutDev L, con
                             to = istar;
                             float rr = 0.0f;
                             if (lane < P && keepE)
-                                rr = lds_f(a_elR_e + istar * 4) * ex2_approx(fminf((e_star - ve_mine) * nb, 0.0f));
+                                rr = lds_f(a_elR_e + istar * 4) * boltz(e_star - ve_mine, nb);
                             from = pick_group<5>(rr, rf);
                             from = (from >= 0) ? from + N : ptop;
                         }
@@ -536,7 +544,7 @@ __global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, co
         }
     }
     __syncwarp();
-    const float nb = -1.4426950408889634f / kT;
+    const float nb = kT;
     for (int idx = lane; idx < S * S; idx += 32) {
         const int i = idx / S, j = idx % S;
         bool ok = (i != j) && !(i >= N && j >= N);
@@ -548,9 +556,9 @@ __global__ void kmc_probe_kernel(const LayoutDev L, const double *E_constant, co
                 const float2 v = L.tblf[j * pitch + i];
                 r = ma(v.x, v.y, se_io[j], se_io[i], nb);
             } else if (i < N) {  // i -> electrode j
-                r = L.tblf[j * pitch + i].x * ex2_approx(fminf((se_io[j] - se_io[i]) * nb, 0.0f));
+                r = L.tblf[j * pitch + i].x * boltz(se_io[j] - se_io[i], nb);
             } else {             // electrode i -> acceptor j
-                r = L.tblf[i * pitch + j].y * ex2_approx(fminf((se_io[j] - se_io[i]) * nb, 0.0f));
+                r = L.tblf[i * pitch + j].y * boltz(se_io[j] - se_io[i], nb);
             }
         }
         rates[idx] = r;

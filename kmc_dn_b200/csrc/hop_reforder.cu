@@ -40,7 +40,8 @@ __global__ void __launch_bounds__(256) kmc_reforder_kernel(const LayoutDev L, co
     float *eps_base = reinterpret_cast<float *>(tbl + S * pitch2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
 
-    for (int idx = tid; idx < S * pitch2; idx += blockDim.x) tbl[idx] = L.tbl[idx];
+    for (int i0 = 0; i0 < S * pitch2; i0 += blockDim.x)  // (thread-independent trip counts: see the staging loop of hop_lanes.cu)
+        if (i0 + tid < S * pitch2) tbl[i0 + tid] = L.tbl[i0 + tid];
     __syncthreads();
 
     const int64_t m = (int64_t)blockIdx.x * nwarps + warp;
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(256) kmc_reforder_kernel(const LayoutDev L, co
         }
     }
 
-    const float negbeta = -1.4426950408889634f / (float)E.kT[m];
+    const float negbeta = (float)E.kT[m];  // kT (the Boltzmann factor takes kT itself: kmc_device.cuh boltz)
     const uint64_t gm = E.member_index0 + (uint64_t)m;
     const uint2 key = make_uint2((uint32_t)E.seed, (uint32_t)(E.seed >> 32));
     const bool inject = E.stream_e != nullptr;

@@ -158,7 +158,7 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
         o.s_true[k] = (float)eps64[k];
         ws_f(a_mir + (lane + 32 * k) * 4, o.s_true[k]);
         src[k] = oc ? o.s_true[k] : -BIGW;       // only occupied acceptors emit to acceptors
-        nbs[k] = oc ? nb : -nb;                  // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
+        nbs[k] = oc ? 1.0f : -1.0f;              // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
         erow[k] = reinterpret_cast<const float *>(tbl + N * PITCH + lane + 32 * k) + (oc ? 0 : 1);
         o.top[k] = 0.0f; o.rest[k] = 0.0f; o.ptn[k] = 0;
     }
@@ -218,8 +218,8 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
             } else {  // electrode j - N: acceptor -> electrode if occupied, electrode -> acceptor if empty
 #pragma unroll
                 for (int k = 0; k < AS; ++k) {
-                    const float tc = (nbs[k] == nb) ? v[k].x : v[k].y;
-                    const float x = tc * ex2_approx(fminf((sj - o.s_true[k]) * nbs[k], 0.0f));
+                    const float tc = (nbs[k] > 0.0f) ? v[k].x : v[k].y;
+                    const float x = tc * boltz((sj - o.s_true[k]) * nbs[k], nb);
                     o.rest[k] += fminf(x, o.top[k]);
                     if (x > o.top[k]) o.ptn[k] = j;
                     o.top[k] = fmaxf(x, o.top[k]);
@@ -250,7 +250,7 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
         const float se = wl_f(a_mir + (32 * AS + e) * 4);
 #pragma unroll
         for (int k = 0; k < AS; ++k) {
-            const float x = erow[k][e * 2 * PITCH] * ex2_approx(fminf((se - o.s_true[k]) * nbs[k], 0.0f));
+            const float x = erow[k][e * 2 * PITCH] * boltz((se - o.s_true[k]) * nbs[k], nb);
             o.rest[k] += fminf(x, o.top[k]);
             if (x > o.top[k]) o.ptn[k] = N + e;
             o.top[k] = fmaxf(x, o.top[k]);
@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
     const uint32_t tbl_bytes = GT ? 0u : (uint32_t)((((size_t)S * PITCH * sizeof(float2)) + 15) & ~size_t(15));
     if (!GT) {
         float2 *stage = reinterpret_cast<float2 *>(smem_raw);
-        for (int idx = tid; idx < S * PITCH; idx += blockDim.x) stage[idx] = L.tblf[idx];
+        for (int i0 = 0; i0 < S * PITCH; i0 += blockDim.x)  // (thread-independent trip counts: see the staging loop of hop_lanes.cu)
+            if (i0 + tid < S * PITCH) stage[i0 + tid] = L.tblf[i0 + tid];
     }
     const uint32_t sb = (uint32_t)__cvta_generic_to_shared(smem_raw);
     const uint32_t wb = sb + tbl_bytes + (uint32_t)warp * G::WARP_BYTES;
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
         const uint32_t gen = (uint32_t)m + 1u;
 
         // ---- member parameters
-        const float nb = -1.4426950408889634f / (float)E.kT[m];
+        const float nb = (float)E.kT[m];  // kT, narrowed as the cgo wrappers do (simulationWrapper.go:92)
         const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;
         __syncwarp();
         ws_f(a_mir + (32 * AS + lane) * 4, ve_mine);
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
                         }
                         if (to < 0) {  // electrode targets: istar -> e
                             float rr = 0.0f;
-                            if (lane < P && (N + lane) != skip) rr = ecol[0] * ex2_approx(fminf((ve_mine - s_star) * nb, 0.0f));
+                            if (lane < P && (N + lane) != skip) rr = ecol[0] * boltz(ve_mine - s_star, nb);
                             const int e = w_pick_group(rr, thr, lane);
                             to = (e >= 0) ? N + e : lastpos;
                         }
@@ -664,7 +665,7 @@ __global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const 
                     } else {  // empty acceptor: events e -> istar
                         to = istar;
                         float rr = 0.0f;
-                        if (lane < P && (N + lane) != skip) rr = ecol[1] * ex2_approx(fminf((s_star - ve_mine) * nb, 0.0f));
+                        if (lane < P && (N + lane) != skip) rr = ecol[1] * boltz(s_star - ve_mine, nb);
                         const int e = w_pick_group(rr, rf, lane);
                         from = (e >= 0) ? N + e : (skip >= 0 ? skip : -1);
                     }

@@ -357,29 +357,30 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                 E.rk[2 * r + 1] = (uint32_t)(a->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
             }
             MemoPlan plan{0, 0};
-            E.lanes_mpb_log = 5;
+            E.lanes_halves = 0;
             le = launch_lanes(D, E, st, nullptr, &plan);
             if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
-            // members per warp: 32; 16 or 8 when full warps would leave more than half of the device's warp slots empty (a warp's
-            // hop costs the same whatever the number of live lanes, so spreading the members costs nothing and halves what a
-            // warp has to evaluate; below 16 the seeds of a voltage vector no longer share one table)
-            // (measured on C3 x 1e5 hops, profiles/r02/exp4_members_per_warp.jsonl: 65 536 members 6.6e10 / 7.7e10 / 5.2e10 hops/s
-            //  with 32 / 16 / 8 members per warp, 32 768: 3.4e10 / 5.0e10 / 4.6e10, 16 384: 1.8e10 / 2.9e10 / 3.2e10)
-            if (2 * ((B + 31) / 32) <= plan.max_slots) E.lanes_mpb_log = 4;
-            if (3 * ((B + 15) / 16) <= plan.max_slots) E.lanes_mpb_log = 3;
-            if (const char *ev = getenv("KMCB200_LANES_MPB_LOG")) E.lanes_mpb_log = std::max(3, std::min(5, atoi(ev)));
-            if (E.lanes_mpb_log != 5) {
+            // An ensemble whose blocks of 32 members would leave more than half of the device's warp slots empty is handed out
+            // in HALVES: a block made of two runs of 16 identical members (two voltage vectors x 16 seeds: nothing shared
+            // between them) is run by two warps, 16 lanes each -- a warp's hop costs the same whatever the number of live lanes
+            // --, a block that is ONE run keeps one warp and one table.  Measured on C3 x 1e5 hops (profiles/r02/
+            // members_per_warp.md): 65 536 members 6.0e10 -> 7.2e10 hops/s, 32 768: 3.4e10 -> 4.9e10; C4 (runs of 1024 seeds):
+            // 1.1e11 either way (9.5e10 when every block was split).
+            if (2 * ((B + 31) / 32) <= plan.max_slots) {
+                E.lanes_halves = 1;
+                if (const char *ev = getenv("KMCB200_LANES_HALVES")) E.lanes_halves = atoi(ev) != 0;
+            }
+            if (E.lanes_halves) {
                 le = launch_lanes(D, E, st, nullptr, &plan);
                 if (le != cudaSuccess) return fail(std::string("kernel plan: ") + cudaGetErrorString(le));
             }
-            const int64_t mpb = (int64_t)1 << E.lanes_mpb_log;
-            const int64_t W = plan.warp_slots, nblocks = (B + mpb - 1) / mpb;
+            const int64_t W = plan.warp_slots, nblocks = (B + 31) / 32;
             // ---- the tail of the queue in slices of hops (hop_lanes.cu, "Scheduling"): with more than one round of blocks
             //      per warp slot the launch would otherwise end on a few warps finishing whole blocks
-            E.lanes_nb_full = nblocks; E.lanes_ns = 1; E.lanes_slice_hops = th; E.lanes_prog = nullptr; E.lanes_ck = nullptr;
+            E.lanes_nb_full = nblocks << E.lanes_halves; E.lanes_ns = 1; E.lanes_slice_hops = th; E.lanes_prog = nullptr; E.lanes_ck = nullptr;
             int ns = (int)std::min<int64_t>(8, th / 8192);
             if (const char *ev = getenv("KMCB200_LANES_SLICES")) ns = atoi(ev);
-            if (ns > 1 && nblocks > W) {
+            if (ns > 1 && nblocks > W && !E.lanes_halves) {  // (halves: the units fit the warp slots, nothing queues)
                 const int64_t nb_sl = nblocks < 3 * W ? nblocks : 2 * W;
                 E.lanes_nb_full = nblocks - nb_sl; E.lanes_ns = ns;
                 E.lanes_slice_hops = ((th + ns - 1) / ns + 63) / 64 * 64;

@@ -44,11 +44,28 @@ __device__ __forceinline__ double warp_incl_scan(double v, int lane) {
     return v;
 }
 
+// Boltzmann factor of the Miller-Abrahams rate: exp(-dE/kT) for dE > 0, else 1 (simulation.go:72-76), with the
+// reference's roundings: q = float32(-dE/kT) (one correctly rounded fp32 division -- exact, and skipped, for kT = 1), then
+// exp(q) = 2^(q * log2e) with the product carried in two floats, so that the argument of ex2.approx is exact to 2^-48 and
+// the result is within ex2.approx's 2^-22 of float32(math.Exp(float64(q))) for EVERY dE, not only for the large rates.
+// kT is warp-uniform wherever this is called.
+__device__ __forceinline__ float boltz(float dE, float kT) {
+#ifdef KMCB200_FAST_BOLTZ  // (A/B measurements only: round 1's three-instruction form, 1e-5 on the smallest rates)
+    return ex2_approx(fminf(dE * (-1.4426950408889634f / kT), 0.0f));
+#endif
+    const float d = fmaxf(dE, 0.0f);
+    const float q = (kT == 1.0f) ? -d : __fdiv_rn(-d, kT);
+    const float hi = q * 1.4426950216293335f;                 // float32(log2 e)
+    float lo = fmaf(q, 1.4426950216293335f, -hi);
+    lo = fmaf(q, 1.9259629911e-8f, lo);                        // log2 e - float32(log2 e)
+    const float t = ex2_approx(hi);
+    return fmaf(t, lo * 0.6931471805599453f, t);
+}
+
 // Miller-Abrahams rate of one pair: v = {nu*tc, I0*R/d (0 unless acceptor-acceptor)}.
-// dE>0 -> exp(-dE/kT), else 1   ==   exp2(min(-dE*log2e/kT, 0)).
-__device__ __forceinline__ float ma_rate(float2 v, float e_to, float e_from, float negbeta) {
+__device__ __forceinline__ float ma_rate(float2 v, float e_to, float e_from, float kT) {
     const float dE = (e_to - e_from) - v.y;
-    return v.x * ex2_approx(fminf(dE * negbeta, 0.0f));
+    return v.x * boltz(dE, kT);
 }
 
 

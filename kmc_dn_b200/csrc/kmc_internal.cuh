@@ -54,7 +54,7 @@ struct EnsembleDev {
     uint32_t rk[20];
     int64_t lanes_nb_full, lanes_slice_hops;
     int lanes_ns;
-    int lanes_mpb_log;   // log2(members per block = per warp): 5, or 4 / 3 when the ensemble would otherwise leave warp slots empty
+    int lanes_halves;    // 1: every block of 32 members is handed out twice and split where a run starts at member 16 (hop_lanes.cu)
     uint32_t *lanes_prog, *lanes_ck;
 };
 

@@ -99,10 +99,10 @@ __device__ __forceinline__ uint32_t bcast_u(uint32_t v, int src, int lane) {
 }
 
 // Miller-Abrahams factor in the reference's operation order (simulation.go:66-77): dE = e_to - e_from - kd,
-// rate = tc * exp(-dE/kT) for dE > 0, else tc.   nb = -log2(e)/kT.
-__device__ __forceinline__ float ma(float tc, float kd, float e_to, float e_from, float nb) {
+// rate = tc * exp(-dE/kT) for dE > 0, else tc (boltz: kmc_device.cuh).
+__device__ __forceinline__ float ma(float tc, float kd, float e_to, float e_from, float kT) {
     const float dE = (e_to - e_from) - kd;
-    return tc * ex2_approx(fminf(dE * nb, 0.0f));
+    return tc * boltz(dE, kT);
 }
 
 // first lane whose inclusive prefix reaches thr among lanes with a positive rate; if rounding put thr past the
@@ -154,7 +154,7 @@ __device__ __forceinline__ void rank_insert(float x, int site, float (&t)[NR], i
 // Sweep: every allowed pair of the current state exactly once.  Per lane (= acceptor): its NR LARGEST rates t[] with
 // the partner sites p[], and the sum of all its other rates (rest).  Publishes the fp32 energies to the warp's mirror.
 template <int PT, int NR>
-__device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double E64, int lane, int N, int P, float nb,
+__device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double E64, int lane, int N, int P, float kT,
                                             uint32_t a_row_me, uint32_t a_mir,
                                             uint32_t a_elF, uint32_t a_elR, float &e_me, float (&t)[NR], int (&p)[NR],
                                             float &rest) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double 
     __syncwarp();
     const bool o = (occ >> lane) & 1u;
     const float src = o ? e_me : -BIGE;         // only occupied acceptors emit to acceptors
-    const float nbs = o ? nb : -nb;             // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
+    const float sg = o ? 1.0f : -1.0f;          // occupied: i->e, dE = V_e - e_i ; empty: e->i, dE = e_i - V_e
     const uint32_t a_el = (o ? a_elF : a_elR) + lane * 4u;
     rest = 0.0f;
 #pragma unroll
@@ -175,17 +175,17 @@ __device__ __forceinline__ void sweep_state(uint32_t occ, uint32_t accm, double 
         mm &= mm - 1;
         const float ej = lds_f(a_mir + j * 4);
         const float2 v = lds_f2(a_row_me + j * ROWB);
-        rank_insert<NR>(ma(v.x, v.y, ej, src, nb), j, t, p, rest);
+        rank_insert<NR>(ma(v.x, v.y, ej, src, kT), j, t, p, rest);
     }
     if (PT > 0) {
 #pragma unroll
         for (int e = 0; e < (PT > 0 ? PT : 1); ++e) {
-            const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
+            const float x = lds_f(a_el + e * ELB) * boltz((lds_f(a_mir + 128 + e * 4) - e_me) * sg, kT);
             rank_insert<NR>(x, N + e, t, p, rest);
         }
     } else {
         for (int e = 0; e < P; ++e) {
-            const float x = lds_f(a_el + e * ELB) * ex2_approx(fminf((lds_f(a_mir + 128 + e * 4) - e_me) * nbs, 0.0f));
+            const float x = lds_f(a_el + e * ELB) * boltz((lds_f(a_mir + 128 + e * 4) - e_me) * sg, kT);
             rank_insert<NR>(x, N + e, t, p, rest);
         }
     }

@@ -33,6 +33,11 @@ def lanes():
         r = lay.run(hops, c["kT"], V[:40], E_constant=E[:40], occupation0=c["occupation"], seed=4, prehops=50, trace=True,
                     want_occupation=True, want_site_energies=True, want_misses=True, kernel="lanes")
         assert np.isfinite(r["time"]).any()
+        # runs of 32 (the second warp of every block returns at once) and of 16 (every block splits); record outputs
+        for rep in (32, 16):
+            Vr = np.tile(c["electrode_v"], (B, 1)) + (np.arange(B) // rep)[:, None]
+            lay.run(hops, c["kT"], Vr, **kw)
+        lay.run(hops, c["kT"], V[:40], E_constant=E[:40], occupation0=c["occupation"], seed=5, record=True, kernel="lanes")
         lay.close()
         print(f"lanes N={N} P={P}: ok", flush=True)
 

@@ -177,9 +177,27 @@ def test_lanes_results_do_not_depend_on_batching_or_kernel_geometry(golden_py):
     a = lay.run(3000, c["kT"], V, E_constant=E, **kw)
     b1 = lay.run(3000, c["kT"], V[:13], E_constant=E[:13], member_index0=0, **kw)
     b2 = lay.run(3000, c["kT"], V[13:], E_constant=E[13:], member_index0=13, **kw)
-    lay.close()
     np.testing.assert_array_equal(a["time"], np.concatenate([b1["time"], b2["time"]]))
     np.testing.assert_array_equal(a["electrode_occupation"], np.concatenate([b1["electrode_occupation"], b2["electrode_occupation"]]))
+    # An ensemble that leaves warp slots empty gives every block of 32 members two warps and splits it where a run starts at
+    # member 16 (hop_lanes.cu, "halves"): blocks that split (runs of 8 or 16), blocks that do not (runs of 32, of 24: member
+    # 16 is inside a run), a ragged last block -- bit-identical with one warp per block (KMCB200_LANES_HALVES=0).
+    import os
+    for rep, Bh in ((8, 100), (16, 112), (32, 96), (24, 120), (1, 49), (16, 17)):
+        Vh = np.tile(c["electrode_v"], (Bh, 1)) + (np.arange(Bh) // rep)[:, None]
+        Eh = np.tile(c["E_constant"], (Bh, 1))
+        res = []
+        for h in ("1", "0"):
+            os.environ["KMCB200_LANES_HALVES"] = h
+            try:
+                res.append(lay.run(3000, c["kT"], Vh, E_constant=Eh, **kw))
+            finally:
+                os.environ.pop("KMCB200_LANES_HALVES", None)
+        for k in res[0]:
+            if isinstance(res[0][k], np.ndarray):
+                np.testing.assert_array_equal(res[0][k], res[1][k], err_msg=f"runs of {rep}, {Bh} members: {k}")
+        assert np.isfinite(res[0]["time"]).all() and (res[0]["time"] > 0).all()
+    lay.close()
 
 
 def test_lanes_superposition_and_prehops(fixtures_subset):

@@ -145,10 +145,11 @@ def test_reference_order_kernel_replays_oracle_until_a_rounding_tie(golden_py):
 
 # ------------------------------------------------------------------ check 2: energies and rates
 def test_fast_kernel_energies_and_rates_vs_oracle(golden_py, fixtures_subset):
-    """Site energies within 1e-6 (relative to the energy scale) of the Go restatement; rate matrices within
-    1e-6 relative when evaluated at identical fp32 energies (an fp32 energy of magnitude 100 kT carries 4e-6
-    kT of rounding, which alone moves exp(-dE/kT) by that much -- the Go reference differs from the numba
-    reference by the same amount), and within 1e-4 end to end."""
+    """north_star check 2: site energies within 1e-6 (relative to the energy scale) of the Go restatement; rate matrices
+    within 1e-6 relative for EVERY entry when evaluated at identical fp32 energies -- the production arithmetic follows the
+    reference's roundings of the exponent (float32(-dE/kT), simulation.go:73; kmc_device.cuh boltz), also for kT != 1 where
+    that is a correctly rounded division; end to end (device energies) within the reference's own fp32 summation noise:
+    the device energies are exact sums, the reference accumulates in fp32 (a few ulp of the largest energy, over kT)."""
     from oracle import oracle
     cases = dict(golden_py)
     for k in ("rnd_min_max/test1", "XOR_wide5M/test2"):
@@ -156,28 +157,21 @@ def test_fast_kernel_energies_and_rates_vs_oracle(golden_py, fixtures_subset):
     rng = np.random.default_rng(0)
     for name, c in cases.items():
         lay = _layout(c)
-        for trial in range(4):
+        for trial in range(6):
             occ = c["occupation"] if trial == 0 else rng.random(c["N"]) < rng.uniform(0.2, 0.95)
-            se_o, r_o = oracle.go_rates(c["N"], c["P"], c["nu"], c["kT"], c["I_0"], c["R"], occ, c["distances"],
+            kT = c["kT"] * (1.0, 1.0, 1.0, 1.0, 0.37, 2.9)[trial]  # (the last two: the division is not exact)
+            se_o, r_o = oracle.go_rates(c["N"], c["P"], c["nu"], kT, c["I_0"], c["R"], occ, c["distances"],
                                         c["E_constant"], c["transitions_constant"], site_energies_of(c))
-            se_d, r_d = lay.probe_rates(c["E_constant"], c["electrode_v"], c["kT"], occ)
+            se_d, r_d = lay.probe_rates(c["E_constant"], c["electrode_v"], kT, occ)
             scale = max(np.abs(c["E_constant"]).max(), 1.0)
             np.testing.assert_allclose(se_d, se_o, rtol=1e-6, atol=1e-6 * scale, err_msg=name)
-            _, r_same = lay.probe_rates(c["E_constant"], c["electrode_v"], c["kT"], occ, site_energies=se_o)
+            _, r_same = lay.probe_rates(c["E_constant"], c["electrode_v"], kT, occ, site_energies=se_o)
             assert ((r_same > 0) == (r_o > 0)).all() or np.abs(r_o[(r_same > 0) != (r_o > 0)]).max() < 1e-37
-            # entries below 2^-24 of the list total cannot move the Go loop's float32 cumulative list at all;
-            # they are checked to 2e-5 (|dE|/kT ~ 60 there: a float32 product dE*(1/kT) alone carries 4e-6)
-            # A float32 exponent argument t = -dE/kT is only known to ulp(t)/2, i.e. the rate to |t|*4e-8 --
-            # for the reference's own float32 loop as much as for this one.  1e-6 therefore holds for the
-            # entries that carry the dynamics (within 2^-12 of the list total, |t| <~ 12); the far tail, which
-            # cannot even move the Go loop's float32 cumulative list, is checked to 1e-5.
-            live = r_o > 2.0 ** -12 * r_o.sum()
-            np.testing.assert_allclose(r_same[live], r_o[live], rtol=1e-6, err_msg=name)
-            live = r_o > 1e-30
-            np.testing.assert_allclose(r_same[live], r_o[live], rtol=1e-5, err_msg=name)
+            live = r_o > 1e-30  # (everything above the range where float32 runs out of exponent)
+            np.testing.assert_allclose(r_same[live], r_o[live], rtol=1e-6, err_msg=f"{name} kT={kT}")
             live = r_o > 1e-9 * r_o.max()
             # end to end (device energies): a few float32 ulps of the largest energy, over kT, in the exponent
-            tol = 6 * float(np.spacing(np.float32(np.abs(se_o).max()))) / c["kT"] + 2e-6
+            tol = 6 * float(np.spacing(np.float32(np.abs(se_o).max()))) / kT + 2e-6
             np.testing.assert_allclose(r_d[live], r_o[live], rtol=tol, err_msg=name)
         lay.close()
 
