@@ -50,7 +50,12 @@ namespace kmcb200 {
 #define WT_KEY 408u    // u32 x 8 key words, then the tag {member + 1, launch id}
 #define WT_GEN 440u
 #define WT_LAUNCH 444u
+#ifndef RING_D
 #define RING_D 4       // rows in flight per warp in the cp.async ring of the GT sweep
+#endif
+#ifndef WIDE_MIN_CTAS
+#define WIDE_MIN_CTAS 3  // 159 registers instead of 211: three CTAs per SM (C5: +20 %, profiles/r02/exp7_wide_occupancy.sh)
+#endif
 
 namespace {
 
@@ -270,7 +275,7 @@ struct WideGeom {
 };
 
 template <int AS, int LOGK, bool DBG, bool GT>
-__global__ void __launch_bounds__(128) kmc_wide_kernel(const LayoutDev L, const EnsembleDev E) {
+__global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const LayoutDev L, const EnsembleDev E) {
     using G = WideGeom<AS, LOGK, GT>;
     constexpr int K = G::K;
     constexpr int PITCH = 32 * AS + 1;

@@ -397,9 +397,11 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             E.gtab = nullptr; E.gtab_log = 6;
             if (!(E.lanes_flags & 1)) {
                 // sets (2 ways x 64 B) per warp slot, shared by the warp's runs of identical members (a run of g members gets
-                // g/32 of them).  A run of 16 seeds visits 60-600 states in 1.6e6 hops; with 2-way LRU sets 2^11 per run
-                // leave next to no conflict misses (profiles/r02/table_model.md)
-                int tlog = th < 3000 ? 9 : (th < 30000 ? 11 : 12);
+                // g/32 of them).  A run of 16 seeds visits 60-600 states in 1.6e6 hops; the handful of sets that three or more
+                // of them hash to keep re-evaluating, so the table is sized well past the state count: C3, 1 048 576 members x
+                // 1e5 hops: 2^11 sets per slot 1.37e11 hops/s, 2^12 1.47e11, 2^13 1.54e11, 2^14 1.54e11, 2^15 1.50e11
+                // (profiles/r02/lanes_generations.md).  2^13 sets x 128 B x 4144 warp slots = 4.3 GB.
+                int tlog = th < 3000 ? 9 : (th < 30000 ? 11 : 13);
                 if (const char *ev = getenv("KMCB200_LTAB_LOG")) tlog = atoi(ev);
                 if (tlog < 6) tlog = 6;
                 if (tlog > 16) tlog = 16;
