@@ -70,7 +70,8 @@ struct LanesGeom {
     static constexpr int MIRB = 256;                        // mirror: acceptor energies (128 B) | electrode energies (128 B)
     static constexpr int RUNB = 128 + 4 * PV + 16;          // per run: E_constant row (f32 x 32) | electrode energies | kT
     static constexpr int TALB = PV * 32 * 4;                // electrode tallies [electrode][trajectory]
-    static constexpr int WARP_BYTES = MIRB + LANES_RMAX * RUNB + TALB;
+    static constexpr int STASHW = 6;                        // words per trajectory parked in shared memory around an evaluation
+    static constexpr int WARP_BYTES = MIRB + LANES_RMAX * RUNB + TALB + STASHW * 128;
 };
 
 struct Sector {
@@ -485,18 +486,14 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
     // TWO warps; if a run of identical members starts at member 16 (two runs of 16 seeds: nothing is shared across the
     // halves), they run 16 members each -- a warp's hop costs the same whatever the number of live lanes --, otherwise
     // the first one runs the whole block and the second one returns (a run of 32 keeps ONE table).
-    const int hl = E.lanes_halves != 0;
-    const bool halves = hl != 0;
-    const int64_t nunits = nblocks << hl;
-    const int64_t nb_full = E.lanes_nb_full, nb_sl = nunits - nb_full;
-    const int64_t n_items = nb_full + nb_sl * ns;
+    const bool halves = E.lanes_halves != 0;
 
     // ---- persistent: every warp pulls work items from the global queue
     //      (halves: every unit has a warp slot of its own -- the host checks it --, so a warp's ONE item is its slot number.
     //      Where no block splits, the live units are then the first halves in the first CTAs, which the hardware spreads evenly
     //      over the SMs; taken from a queue by 4096 warps arriving together, the live warps per SM came out binomial.)
     if (halves) {
-        if (wslot >= nunits) return;
+        if (wslot >= 2 * nblocks) return;
         if (wslot >= nblocks) {  // a second half lives only if a run starts at member 16 of its block
             const int64_t m16 = ((wslot - nblocks) << 5) + 16;
             if (m16 >= E.B) return;
@@ -509,19 +506,18 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             if (__all_sync(FULL, same)) return;
         }
     }
-    bool own_item = halves;
+    // (what follows keeps nothing of this bookkeeping in registers across the hop loop: everything is re-derived from the
+    // kernel parameters per item -- the hop loop spills at the slightest provocation)
     for (;;) {
         int64_t item;
-        if (own_item) {
-            item = wslot;
-            own_item = false;
-        } else {
-            if (halves) break;
+        if (E.lanes_halves) item = wslot;
+        else {
             unsigned long long mq = 0;
             if (lane == 0) mq = atomicAdd(E.queue, 1ULL);
             item = (int64_t)__shfl_sync(FULL, mq, 0);
         }
-        if (item >= n_items) break;
+        const int64_t nb_full = E.lanes_nb_full, nb_sl = (nblocks << (E.lanes_halves != 0)) - nb_full;
+        if (item >= nb_full + nb_sl * ns) break;
         int64_t unit;
         int hA, hB;
         int s0 = 0, s1 = ns;
@@ -537,6 +533,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             hA = s0 * (int)E.lanes_slice_hops;
             hB = (s1 == ns) ? total_hops : s1 * (int)E.lanes_slice_hops;
         }
+        const int prog_ix = (int)(unit - nb_full);  // (sliced units: < 2^31 of them)
         // (first halves first, see the queue above)
         const int half = (int)(unit >= nblocks);
         const int64_t blk = unit - (half ? nblocks : 0);
@@ -618,7 +615,7 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
                 for (int i = 0; i < N; ++i) E.avg_occupation[m * N + i] = 0.0;
         } else {
             if (lane == 0) {
-                const volatile uint32_t *pr = E.lanes_prog + (unit - nb_full);
+                const volatile uint32_t *pr = E.lanes_prog + prog_ix;
                 while (*pr < (uint32_t)s0) __nanosleep(200);
             }
             __syncwarp();
@@ -661,7 +658,14 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         uint32_t rt = f1;                                                                                              \
         const uint32_t st = (f0 != occ) ? 1u : (X > f7 ? 2u : 0u);                                                     \
         if (__any_sync(FULL, st != 0)) {                                                                               \
+            /* hop-loop bookkeeping the evaluation does not need waits in shared memory meanwhile: ptxas otherwise */   \
+            /* spills it for good and reloads it in EVERY hop (2-3 LDL per hop in front of the loop branch) */         \
+            const uint32_t a_st = a_tal_me + G::TALB;                                                                  \
+            sts_u(a_st, (uint32_t)q1); sts_u(a_st + 128u, blk0); sts_u(a_st + 256u, gm_lo);                            \
+            sts_u(a_st + 384u, gm_hi); sts_u(a_st + 512u, (uint32_t)hend); sts_u(a_st + 640u, (uint32_t)h0);           \
             const uint2 r = lanes_cold<PT, DBG, NR>(E, ctx, occ, xr, st, f1, f7, ri, setofs, leader);                  \
+            q1 = (int)lds_u(a_st); blk0 = lds_u(a_st + 128u); gm_lo = lds_u(a_st + 256u);                              \
+            gm_hi = lds_u(a_st + 384u); hend = (int)lds_u(a_st + 512u); h0 = (int)lds_u(a_st + 640u);                  \
             if (st) {                                                                                                  \
                 code = r.x;                                                                                            \
                 rt = r.y;                                                                                              \
@@ -722,8 +726,9 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             int hend = (h0 | 63) + 1;
             if (hend > hB) hend = hB;
             if (h0 < prehops && hend > prehops) hend = prehops;
-            const int q0 = h0 & 63, q1 = q0 + (hend - h0);
-            const uint32_t blk0 = (uint32_t)(h0 >> 6) * 32u;  // (< 2^30: the counter's second word stays 0)
+            const int q0 = h0 & 63;
+            int q1 = q0 + (hend - h0);
+            uint32_t blk0 = (uint32_t)(h0 >> 6) * 32u;  // (< 2^30: the counter's second word stays 0)
             uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
             for (int q = q0; q < q1 && !stop; ++q) {
                 uint32_t er, xq;
@@ -764,10 +769,11 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
             }
         }
         if (last && E.site_energies_out) {
+            const uint32_t actm = __ballot_sync(FULL, active);
             for (int t = 0; t < 32; ++t) {
                 const int64_t mt = base + t;
                 if (mt >= E.B) break;
-                if (split && (t >> 4) != half) continue;
+                if (!((actm >> t) & 1u)) continue;  // (the other half of a split block)
                 const uint32_t occu = __shfl_sync(FULL, occ, t);
                 double E64;
                 float ve_t, kTt;
@@ -779,10 +785,11 @@ __global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const La
         if (!last) {
             __threadfence();
             __syncwarp();
-            if (lane == 0) atomicExch(E.lanes_prog + (unit - nb_full), (uint32_t)s1);
+            if (lane == 0) atomicExch(E.lanes_prog + prog_ix, (uint32_t)s1);
         }
         __syncwarp();
 #undef LANES_SET
+        if (E.lanes_halves) break;  // (one unit per warp slot)
     }  // work items
 }
 
