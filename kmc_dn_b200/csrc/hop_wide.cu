@@ -53,6 +53,16 @@ namespace kmcb200 {
 #ifndef RING_D
 #define RING_D 4       // rows in flight per warp in the cp.async ring of the GT sweep
 #endif
+#ifndef SPC
+#define SPC 32
+#endif
+#ifndef SP_LOGK
+#define SP_LOGK 4
+#endif
+#ifndef SP_MIN_CTAS
+#define SP_MIN_CTAS 3
+#endif
+// SPC: pairs per lane parked between two evaluation rounds of the sparse sweep
 #ifndef WIDE_MIN_CTAS
 #define WIDE_MIN_CTAS 3  // 159 registers instead of 211: three CTAs per SM (C5: +20 %, profiles/r02/exp7_wide_occupancy.sh)
 #endif
@@ -133,10 +143,19 @@ struct SweepOut {
 
 // Brings the fp64 energies from the mask of the last sweep (occ_sw) to the mask occ, publishes them, and evaluates
 // every allowed pair of the state exactly once (hop_fast.cu's sweep).
-template <int AS, bool GT>
+//
+// SP (sparse pair table: a layout built with a prune threshold, simulation.go:200-215 -- a pruned pair is an EXACT zero there
+// and here): the sweep visits only the pairs whose table entry is not zero.  near[j][lane] holds, as bits k, which of the
+// lane's acceptors lane + 32k have a non-zero constant towards target j (either direction for an electrode row).  For every
+// target row the lane parks its (row, k) pairs in a list; when a list is nearly full, and at the end, all lanes evaluate their
+// lists side by side (table entries straight from L1/L2, two loads ahead of the arithmetic) into per-lane accumulators in
+// shared memory.  Per (lane, k) the pairs arrive in the dense sweep's order and a zero pair changes nothing there
+// (rest += min(0, top); 0 > top is false), so the result is BIT-IDENTICAL to the dense sweep (tests/test_gpu_parity.py);
+// a miss costs O(non-zero pairs of the state) -- C5 at prune_threshold 1e-7: ~330 pairs instead of 8 400.
+template <int AS, bool GT, bool SP>
 __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, int P, int lane, float nb, const uint32_t (&accm)[AS],
                                            const uint32_t (&occ)[AS], uint32_t (&occ_sw)[AS], double (&eps64)[AS],
-                                           uint32_t a_mir, uint32_t a_ring, SweepOut<AS> &o) {
+                                           uint32_t a_mir, uint32_t a_ring, uint32_t a_near, SweepOut<AS> &o) {
     // ---- energies: flip the sites that differ (simulation.go:107-130, applied exactly)
 #pragma unroll
     for (int kw = 0; kw < AS; ++kw) {
@@ -168,7 +187,100 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
         o.top[k] = 0.0f; o.rest[k] = 0.0f; o.ptn[k] = 0;
     }
     __syncwarp();
-    if (GT) {
+    if (SP) {
+        const uint32_t a_top = a_ring, a_rest = a_ring + AS * 128, a_ptn = a_ring + 2 * AS * 128;
+        const uint32_t a_pl = a_ring + 3 * AS * 128;  // parked pairs [slot][lane], u16 = row << 3 | k
+        const uint32_t a_list = a_pl + SPC * 64;      // u16 row indices: empties in ascending order, then N + e
+        uint32_t occm8 = 0, valid8 = 0;
+#pragma unroll
+        for (int k = 0; k < AS; ++k) {
+            occm8 |= ((occ[k] >> lane) & 1u) << k;
+            valid8 |= ((accm[k] >> lane) & 1u) << k;
+            ws_f(a_top + (k * 32 + lane) * 4, 0.0f);
+            ws_f(a_rest + (k * 32 + lane) * 4, 0.0f);
+            ws_u(a_ptn + (k * 32 + lane) * 4, 0u);
+        }
+        int n_emp = 0;
+#pragma unroll
+        for (int kw = 0; kw < AS; ++kw) {
+            const uint32_t w = ~occ[kw] & accm[kw];
+            if ((w >> lane) & 1u) {
+                const int pos = n_emp + __popc(w & ((1u << lane) - 1u));
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_list + 2u * (uint32_t)pos), "h"((unsigned short)(kw * 32 + lane)));
+            }
+            n_emp += __popc(w);
+        }
+        if (lane < P) asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_list + 2u * (uint32_t)(n_emp + lane)), "h"((unsigned short)(N + lane)));
+        __syncwarp();
+        const int T = n_emp + P;
+        auto row_of = [&](int t) {
+            unsigned short jr;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(jr) : "r"(a_list + 2u * (uint32_t)t));
+            return (int)jr;
+        };
+        int n = 0;
+        auto fetch = [&](int e) {  // table entry of this lane's parked pair e
+            float2 v = make_float2(0.0f, 0.0f);
+            if (e < n) {
+                unsigned short pr;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pr) : "r"(a_pl + (uint32_t)(e * 32 + lane) * 2u));
+                v = __ldg(tbl + row_of((int)pr >> 3) * PITCH + lane + 32 * ((int)pr & 7));
+            }
+            return v;
+        };
+        for (int t = 0;; ++t) {
+            const bool done = t >= T;
+            if (!done) {
+                const int j = row_of(t);
+                uint32_t m8;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m8) : "r"(a_near + (uint32_t)j * 32u + (uint32_t)lane));
+                m8 &= (t < n_emp) ? occm8 : valid8;
+                while (m8) {
+                    const int k = __ffs(m8) - 1;
+                    m8 &= m8 - 1;
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(a_pl + (uint32_t)(n * 32 + lane) * 2u), "h"((unsigned short)((t << 3) | k)));
+                    ++n;
+                }
+            }
+            if (done || __any_sync(FULL, n > SPC - AS)) {
+                const int nmax = __reduce_max_sync(FULL, n);
+                float2 va = fetch(0), vb = fetch(1);
+                for (int e = 0; e < nmax; ++e) {
+                    const float2 v = va;
+                    va = vb;
+                    vb = fetch(e + 2);
+                    if (e < n) {
+                        unsigned short pr;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(pr) : "r"(a_pl + (uint32_t)(e * 32 + lane) * 2u));
+                        const int k = (int)pr & 7, j = row_of((int)pr >> 3);
+                        const float si = wl_f(a_mir + (lane + 32 * k) * 4);
+                        float x;
+                        if (j < N) x = ma_rate(v, wl_f(a_mir + j * 4), si, nb);
+                        else {
+                            const float se = wl_f(a_mir + (32 * AS + (j - N)) * 4);
+                            const bool oc = (occm8 >> k) & 1u;  // occupied: i -> e, dE = V_e - e_i; empty: e -> i, dE = e_i - V_e
+                            x = (oc ? v.x : v.y) * boltz(oc ? se - si : si - se, nb);
+                        }
+                        const uint32_t a = (uint32_t)(k * 32 + lane) * 4u;
+                        const float top = wl_f(a_top + a);
+                        ws_f(a_rest + a, wl_f(a_rest + a) + fminf(x, top));
+                        if (x > top) {
+                            ws_u(a_ptn + a, (uint32_t)j);
+                            ws_f(a_top + a, x);
+                        }
+                    }
+                }
+                n = 0;
+            }
+            if (done) break;
+        }
+#pragma unroll
+        for (int k = 0; k < AS; ++k) {
+            o.top[k] = wl_f(a_top + (k * 32 + lane) * 4);
+            o.rest[k] = wl_f(a_rest + (k * 32 + lane) * 4);
+            o.ptn[k] = (int)wl_u(a_ptn + (k * 32 + lane) * 4);
+        }
+    } else if (GT) {
         // The pair table lives in global memory (L2): the rows of the state's targets -- its empty acceptors, then the
         // electrodes -- are streamed through a per-warp ring in shared memory with cp.async, RING_D rows ahead of the
         // arithmetic.  Every lane copies exactly the elements it consumes itself (columns lane + 32k), so
@@ -266,17 +378,18 @@ __device__ __forceinline__ void wide_sweep(const float2 *tbl, int PITCH, int N, 
 
 }  // namespace
 
-template <int AS, int LOGK, bool GT>
+template <int AS, int LOGK, bool GT, bool SP = false>
 struct WideGeom {
     static constexpr int K = LOGK >= 0 ? (1 << LOGK) : 0;
     static constexpr int MIRW = 32 * AS + 32;  // per-warp mirror: acceptor energies [0,32*AS), electrode energies after
-    static constexpr int RINGB = GT ? RING_D * AS * 256 + 2 * (32 * AS + 32) : 0;  // row ring + row-index list
+    // row ring + row-index list; sparse sweep: accumulators (top, rest, partner) + parked pairs + row-index list
+    static constexpr int RINGB = SP ? 3 * AS * 128 + SPC * 64 + 2 * (32 * AS + 32) : (GT ? RING_D * AS * 256 + 2 * (32 * AS + 32) : 0);
     static constexpr int WARP_BYTES = MIRW * 4 + 1024 + (K > 0 ? K : 1) * (int)WENT + RINGB;  // mirror | variates | entries | ring
 };
 
-template <int AS, int LOGK, bool DBG, bool GT>
-__global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const LayoutDev L, const EnsembleDev E) {
-    using G = WideGeom<AS, LOGK, GT>;
+template <int AS, int LOGK, bool DBG, bool GT, bool SP>
+__global__ void __launch_bounds__(128, SP ? SP_MIN_CTAS : WIDE_MIN_CTAS) kmc_wide_kernel(const LayoutDev L, const EnsembleDev E) {
+    using G = WideGeom<AS, LOGK, GT, SP>;
     constexpr int K = G::K;
     constexpr int PITCH = 32 * AS + 1;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -285,7 +398,15 @@ __global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const Layo
     const int N = L.N, S = L.S, P = L.P;
     const int tid = threadIdx.x, lane = tid & 31, nwarps = blockDim.x >> 5;
     const int warp = __shfl_sync(FULL, tid >> 5, 0);
-    const uint32_t tbl_bytes = GT ? 0u : (uint32_t)((((size_t)S * PITCH * sizeof(float2)) + 15) & ~size_t(15));
+    // (sparse sweep: the CTA's copy of the near masks takes the place of the table)
+    const uint32_t tbl_bytes = SP ? (uint32_t)(((size_t)S * 32 + 15) & ~size_t(15))
+                                  : (GT ? 0u : (uint32_t)((((size_t)S * PITCH * sizeof(float2)) + 15) & ~size_t(15)));
+    if (SP) {
+        uint32_t *stage = reinterpret_cast<uint32_t *>(smem_raw);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(L.near);
+        for (int i0 = 0; i0 < S * 8; i0 += blockDim.x)
+            if (i0 + tid < S * 8) stage[i0 + tid] = src[i0 + tid];
+    }
     if (!GT) {
         float2 *stage = reinterpret_cast<float2 *>(smem_raw);
         for (int i0 = 0; i0 < S * PITCH; i0 += blockDim.x)  // (thread-independent trip counts: see the staging loop of hop_lanes.cu)
@@ -431,7 +552,7 @@ __global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const Layo
                     if (!hit2) {
                         if (DBG) ++n_miss;
                         SweepOut<AS> sw;
-                        wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sw);
+                        wide_sweep<AS, GT, SP>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sb, sw);
                         // the lane's top event and everything else
                         int ktop = 0;
                         float top = sw.top[0];
@@ -554,7 +675,7 @@ __global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const Layo
                     const uint32_t a_ent = a_cache + (LOGK > 0 ? (Hu >> (32 - (LOGK > 0 ? LOGK : 1))) : 0u) * WENT;
                     if (DBG && hit) ++n_miss;
                     SweepOut<AS> sw;
-                    wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sw);
+                    wide_sweep<AS, GT, SP>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sb, sw);
                     const double total = wl_d(a_ent + WT_TOTAL);
                     int ktop = 0;
                     {
@@ -739,7 +860,7 @@ __global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const Layo
             for (int k = 0; k < AS; ++k) occ[k] = __reduce_or_sync(FULL, lane == k ? occw : 0u);
             if (E.site_energies_out) {  // energies of the final mask
                 SweepOut<AS> sw;
-                wide_sweep<AS, GT>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sw);
+                wide_sweep<AS, GT, SP>(tbl, PITCH, N, P, lane, nb, accm, occ, occ_sw, eps64, a_mir, a_ring, sb, sw);
             }
 #pragma unroll
             for (int k = 0; k < AS; ++k) {
@@ -757,14 +878,15 @@ __global__ void __launch_bounds__(128, WIDE_MIN_CTAS) kmc_wide_kernel(const Layo
     }  // members of this warp slot
 }
 
-template <int AS, int LOGK, bool GT>
+template <int AS, int LOGK, bool GT, bool SP>
 static cudaError_t launch_wide_t(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches, MemoPlan *plan_only) {
-    using G = WideGeom<AS, LOGK, GT>;
+    using G = WideGeom<AS, LOGK, GT, SP>;
     const bool dbg = E.avg_occupation || E.traffic || E.trace || E.stream_e || E.misses;
     int warps = 4;
     while (warps > 1 && (E.B + warps - 1) / warps < 2 * 148) warps >>= 1;
-    const size_t smem = (GT ? 0 : ((((size_t)L.S * (32 * AS + 1) * sizeof(float2)) + 15) & ~size_t(15))) + (size_t)warps * G::WARP_BYTES;
-    auto kern = dbg ? kmc_wide_kernel<AS, LOGK, true, GT> : kmc_wide_kernel<AS, LOGK, false, GT>;
+    const size_t smem = (SP ? (((size_t)L.S * 32 + 15) & ~size_t(15)) : (GT ? 0 : ((((size_t)L.S * (32 * AS + 1) * sizeof(float2)) + 15) & ~size_t(15)))) +
+                        (size_t)warps * G::WARP_BYTES;
+    auto kern = dbg ? kmc_wide_kernel<AS, LOGK, true, GT, SP> : kmc_wide_kernel<AS, LOGK, false, GT, SP>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return err;
     int dev = 0, sms = 0, per_sm = 0;
@@ -784,10 +906,10 @@ static cudaError_t launch_wide_t(const LayoutDev &L, const EnsembleDev &E, cudaS
     return cudaGetLastError();
 }
 
-template <int AS, bool GT>
+template <int AS, bool GT, bool SP = false>
 static cudaError_t launch_wide_k(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches, MemoPlan *plan) {
-    if (logk < 0) return launch_wide_t<AS, -1, GT>(L, E, st, launches, plan);
-    return launch_wide_t<AS, 4, GT>(L, E, st, launches, plan);
+    if (logk < 0) return launch_wide_t<AS, -1, GT, SP>(L, E, st, launches, plan);
+    return launch_wide_t<AS, SP ? SP_LOGK : 4, GT, SP>(L, E, st, launches, plan);
 }
 
 // 32 <= N <= 256 acceptors (N <= 31 runs hop_memo.cu).  logk < 0 disables the memoisation (every hop a miss).
@@ -803,8 +925,11 @@ cudaError_t launch_wide(const LayoutDev &L, const EnsembleDev &E, int logk, cuda
     if (L.pitchf != 32 * (as == 3 ? 4 : (as > 4 ? 8 : as)) + 1) return cudaErrorInvalidValue;
     if (as <= 1) return launch_wide_k<1, false>(L, E, logk, st, launches, plan);
     if (as == 2) return launch_wide_k<2, false>(L, E, logk, st, launches, plan);
-    if (as <= 4) return launch_wide_k<4, true>(L, E, logk, st, launches, plan);
-    return launch_wide_k<8, true>(L, E, logk, st, launches, plan);
+    // a pair table that is mostly zeros (a prune threshold was given): the sweep walks the non-zero pairs only
+    bool sparse = L.sparse != 0;
+    if (const char *ev = getenv("KMCB200_WIDE_SPARSE")) sparse = atoi(ev) != 0 && L.near != nullptr;
+    if (as <= 4) return sparse ? launch_wide_k<4, true, true>(L, E, logk, st, launches, plan) : launch_wide_k<4, true>(L, E, logk, st, launches, plan);
+    return sparse ? launch_wide_k<8, true, true>(L, E, logk, st, launches, plan) : launch_wide_k<8, true>(L, E, logk, st, launches, plan);
 }
 
 }  // namespace kmcb200

@@ -168,7 +168,18 @@ extern "C" kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const
             } else if (keep[(size_t)j * S + i]) v.y = D.nu32 * tc32[(size_t)j * S + i];
             tblf[(size_t)j * D.pitchf + i] = v;
         }
-    int rc = upload(&D.tblf, tblf) || upload(&D.tbl, tbl) || upload(&D.d32, d32) || upload(&D.tc32, tc32) || upload(&D.d64, d64) ||
+    // near masks of the sparse sweep (hop_wide.cu): which of a lane's acceptors have a non-zero constant towards row j
+    std::vector<unsigned char> near((size_t)S * 32, 0);
+    size_t nnz = 0;
+    for (int j = 0; j < S; ++j)
+        for (int i = 0; i < N; ++i) {
+            const float2 v = tblf[(size_t)j * D.pitchf + i];
+            const bool nz = j < N ? v.x != 0.0f : (v.x != 0.0f || v.y != 0.0f);
+            if (nz) near[(size_t)j * 32 + (i & 31)] |= (unsigned char)(1u << (i >> 5));
+            if (nz && j < N) ++nnz;
+        }
+    D.sparse = (N > 64 && 3 * nnz <= (size_t)N * (N - 1)) ? 1 : 0;
+    int rc = upload(&D.near, near) || upload(&D.tblf, tblf) || upload(&D.tbl, tbl) || upload(&D.d32, d32) || upload(&D.tc32, tc32) || upload(&D.d64, d64) ||
              upload(&D.tc64, tc64) || upload(&D.pairs, pairs);
     if (rc) {
         delete lay;
@@ -180,7 +191,7 @@ extern "C" kmcb200_layout *kmcb200_layout_create(int device, int N, int P, const
 extern "C" void kmcb200_layout_destroy(kmcb200_layout *lay) {
     if (!lay) return;
     cudaSetDevice(lay->device);
-    cudaFree(lay->dev.tbl); cudaFree(lay->dev.tblf); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
+    cudaFree(lay->dev.tbl); cudaFree(lay->dev.tblf); cudaFree(lay->dev.near); cudaFree(lay->dev.d32); cudaFree(lay->dev.tc32);
     cudaFree(lay->dev.d64); cudaFree(lay->dev.tc64); cudaFree(lay->dev.pairs);
     cudaFree(lay->ws);
     if (lay->busy_recorded) cudaEventSynchronize(lay->busy);

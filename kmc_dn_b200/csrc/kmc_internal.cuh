@@ -19,6 +19,10 @@ struct LayoutDev {
     //   target j >= N : { nu*tc[i][j], nu*tc[j][i] }        (acceptor i <-> electrode j-N, both directions)
     float2 *tblf;
     int pitchf;
+    // sparse sweep of hop_wide.cu: near[j*32 + lane] = bits k: tblf[j*pitchf + lane + 32k] holds a non-zero constant (for an
+    // electrode row: in either direction); sparse = 1 if at most a third of the acceptor-acceptor constants are non-zero
+    unsigned char *near;
+    int sparse;
     // replay tables (row-major, exactly the caller's values)
     float *d32, *tc32;       // [S*S] narrowed (Go semantics)
     double *d64, *tc64;      // [S*S] (numba semantics)

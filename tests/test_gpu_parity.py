@@ -876,3 +876,34 @@ def test_host_class_simulation_entry_points(fixtures_subset):
     assert r["current"].shape == (32, 8) and np.isfinite(r["current"]).all()
     cur0 = r["current"].reshape(8, 4, 8).mean(1)[:, 0]
     assert cur0[0] > 0 > cur0[-1] or cur0[0] < 0 < cur0[-1]  # the swept electrode's current changes sign with its bias
+
+
+def test_wide_sparse_sweep_is_bit_identical():
+    """A layout built with a prune threshold (simulation.go:200-215) has a pair table that is mostly exact zeros; hop_wide.cu then
+    walks the non-zero pairs only (a miss costs O(neighbours)).  Trace, time, tallies, occupation and energies must be
+    bit-identical with the dense sweep over every (occupied, empty) pair (KMCB200_WIDE_SPARSE=0) -- 256 acceptors (8 per lane)
+    and 100 (4 per lane), cache on and off, thresholds that leave ~5 % and ~1 % of the pairs."""
+    import os
+    from kmc_dn_b200 import workloads
+    from kmc_dn_b200.ensemble import Layout, last_kernel
+
+    for N, M, cut in ((256, 25, 1e-7), (256, 25, 1e-4), (100, 10, 1e-7), (256, 25, 0.0)):
+        w = workloads.c5_scaling(N=N, M=M, B=24)
+        lt = w["tables"]
+        lay = Layout(lt.N, lt.P, lt.distances, lt.transitions_constant, nu=lt.nu, I_0=lt.I_0, R=lt.R, prune_threshold=cut)
+        res = {}
+        for sparse in ("1", "0"):
+            for memo in (True, False):
+                os.environ["KMCB200_WIDE_SPARSE"] = sparse
+                try:
+                    res[sparse, memo] = lay.run(600, w["kT"][:24], w["V"][:24], basis=lt.basis, occupation0=w["occupation0"], seed=5,
+                                                memo=memo, trace=True, want_occupation=True, want_site_energies=True)
+                finally:
+                    os.environ.pop("KMCB200_WIDE_SPARSE", None)
+                assert last_kernel() == "kmc_wide_kernel"
+        ref = res["0", False]
+        assert np.isfinite(ref["time"]).all() and (ref["time"] > 0).all()
+        for key, r in res.items():
+            for k in ("time", "electrode_occupation", "occupation", "trace", "site_energies"):
+                np.testing.assert_array_equal(r[k], ref[k], err_msg=f"N={N} cut={cut} sparse,memo={key}: {k}")
+        lay.close()
