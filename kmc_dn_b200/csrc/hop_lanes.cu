@@ -61,7 +61,9 @@ namespace kmcb200 {
 #define LANES_MIN_CTAS 7  // resident CTAs of 4 warps per SM the register budget is set for (72 registers: measured 1.60e11 hops/s on C3 against 1.26e11 with 8 CTAs / 64 registers -- spills in the hop loop -- and 1.57e11 with 6)
 #endif
 #define LANES_K 14        // events per entry
-#define LANES_RMAX 8      // runs of a warp whose parameters live in shared memory (later runs: from global memory)
+#ifndef LANES_RMAX
+#define LANES_RMAX 6      // runs of a warp whose parameters live in shared memory (later runs: from global memory); 6 keeps 7 CTAs within the 164 KB carve-out step: 88 instead of 56 KB of L1, +2 % (profiles/r02/exp8_lanes_l1.sh)
+#endif
 #define LN2F 0.6931471805599453
 
 template <int PT>
