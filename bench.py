@@ -28,7 +28,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "aggregate KMC hops/s over ensemble"
 UNIT = "hops/s"
-DTYPE = ("f32 rates (ex2.approx) and per-acceptor sums; f64 site energies and total rate; event thresholds 2^-20 fixed point + "
+DTYPE = ("f32 rates (correctly rounded f32 quotient dE/kT, two-float exponent product, ex2.approx) and per-acceptor sums; f64 site energies and total rate; event thresholds 2^-20 fixed point + "
          "exact fp64 tail; dwell = lg2.approx(f32 uniform) x f32(-ln2/total), f32 partial sums per 64 hops, f64 elapsed time")
 
 
