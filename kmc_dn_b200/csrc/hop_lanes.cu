@@ -57,13 +57,21 @@
 namespace kmcb200 {
 
 #define LSETB 128u  // bytes per set (2 ways x 64 B)
+// Launch geometry: 28 warps per SM at 72 registers (measured 1.60e11 hops/s on C3 against 1.26e11 with 32 warps / 64 registers --
+// spills in the hop loop -- and 1.57e11 with 24 / 80), in CTAs of 14 warps: the layout tables (10 KB) are per CTA, and two CTAs of
+// 14 warps need 117 KB of shared memory where seven of 4 need 168 -- the carve-out drops from 196 to 132 KB and L1 grows from 56
+// to 124 KB.  C3 1 048 576 x 1e5: +1 %; 65 536 x 1e6: +8 %; 32 768 x 1e5: +6 %; C4: +6 %; one CTA of 28 warps: +2 % / +10 % / -20 % /
+// -29 % (profiles/r02/exp8_lanes_l1.sh).
+#ifndef LANES_WARPS
+#define LANES_WARPS 14    // warps per CTA
+#endif
 #ifndef LANES_MIN_CTAS
-#define LANES_MIN_CTAS 7  // resident CTAs of 4 warps per SM the register budget is set for (72 registers: measured 1.60e11 hops/s on C3 against 1.26e11 with 8 CTAs / 64 registers -- spills in the hop loop -- and 1.57e11 with 6)
+#define LANES_MIN_CTAS 2  // resident CTAs per SM the register budget is set for
+#endif
+#ifndef LANES_RMAX
+#define LANES_RMAX 8      // runs of a warp whose parameters live in shared memory (later runs: from global memory)
 #endif
 #define LANES_K 14        // events per entry
-#ifndef LANES_RMAX
-#define LANES_RMAX 6      // runs of a warp whose parameters live in shared memory (later runs: from global memory); 6 keeps 7 CTAs within the 164 KB carve-out step: 88 instead of 56 KB of L1, +2 % (profiles/r02/exp8_lanes_l1.sh)
-#endif
 #define LN2F 0.6931471805599453
 
 template <int PT>
@@ -423,7 +431,7 @@ __device__ __forceinline__ uint2 lanes_cold(const EnsembleDev &E, const LaneCtx 
 }
 
 template <int PT, bool DBG, int NR>
-__global__ void __launch_bounds__(128, LANES_MIN_CTAS) kmc_lanes_kernel(const LayoutDev L, const __grid_constant__ EnsembleDev E) {
+__global__ void __launch_bounds__(32 * LANES_WARPS, LANES_MIN_CTAS) kmc_lanes_kernel(const LayoutDev L, const __grid_constant__ EnsembleDev E) {
     using G = LanesGeom<PT>;
     constexpr int PV = G::PV;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -800,7 +808,7 @@ static cudaError_t launch_lanes_t(const LayoutDev &L, const EnsembleDev &E, cuda
     using G = LanesGeom<PT>;
     // (record outputs, injected streams and the table-off switch exist only in the DBG instantiation)
     const bool dbg = E.trace || E.misses || (E.lanes_flags & 1) || E.traffic || E.avg_occupation || E.stream_e;
-    const int warps = 4;
+    const int warps = LANES_WARPS;
     const size_t smem = (((size_t)L.N * ROWB + 2 * (size_t)L.P * ELB + 15) & ~size_t(15)) + (size_t)warps * G::WARP_BYTES;
     // candidates per acceptor for the K largest events of a state
     const int nr = L.N <= 12 ? 3 : 2;
