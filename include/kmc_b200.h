@@ -124,7 +124,11 @@ enum {
                                      bit-identical either way; for testing and profiling)                */
     KMCB200_FLAG_LANES = 4,       /* MODE_FAST, N <= 31, fewer than 2^31 hops: force the thread-per-trajectory kernel
                                      (default: chosen for ensembles of >= 12288 members)                     */
-    KMCB200_FLAG_NO_LANES = 8     /* MODE_FAST: never use the thread-per-trajectory kernel                 */
+    KMCB200_FLAG_NO_LANES = 8,    /* MODE_FAST: never use the thread-per-trajectory kernel                 */
+    KMCB200_FLAG_SOLO = 16,       /* MODE_FAST, N <= 31, fewer than 2^31 hops, no record / trace / injected-stream outputs:
+                                     force the latency kernel (one warp per trajectory, the visited states as a graph in
+                                     shared memory; default: chosen for ensembles of at most 2 members per SM)         */
+    KMCB200_FLAG_NO_SOLO = 32     /* MODE_FAST: never use the latency kernel                                       */
 };
 
 typedef struct {

@@ -16,6 +16,8 @@ FLAG_DEVICE_PTRS = 1
 FLAG_NO_MEMO = 2
 FLAG_LANES = 4      # force the thread-per-trajectory kernel (hop_lanes.cu)
 FLAG_NO_LANES = 8   # never use it
+FLAG_SOLO = 16      # force the latency kernel (kmc_solo_kernel: a few trajectories, one warp each)
+FLAG_NO_SOLO = 32   # never use it
 
 
 class GoSlice(C.Structure):

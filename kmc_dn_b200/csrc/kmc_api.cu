@@ -361,12 +361,32 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                 if (const char *ev = getenv("KMCB200_LANES")) lanes = atoi(ev) != 0;
             }
         }
-        if (lanes) {
+        // ---- latency kernel: a few trajectories (the drop-in's single go_simulation call), one warp each, the visited states
+        //      as a graph in shared memory (hop_lanes.cu, kmc_solo_kernel): 3 x faster per trajectory than a warp of the
+        //      memoised kernel as long as every trajectory has a CTA of its own
+        bool solo = false;
+        {
+            const bool solo_ok = narrow && th < kLanesMaxHops && !(a->flags & KMCB200_FLAG_NO_MEMO) && !E.trace && !E.misses &&
+                                 !E.traffic && !E.avg_occupation && !E.stream_e;
+            if (a->flags & KMCB200_FLAG_SOLO) {
+                if (!solo_ok) return fail("kmcb200_run_ensemble: the latency kernel needs N <= 31, fewer than 2^31 hops and no record / trace / stream outputs");
+                solo = true;
+            } else if (solo_ok && !(a->flags & (KMCB200_FLAG_NO_SOLO | KMCB200_FLAG_LANES))) {
+                int sms = 0;
+                cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, lay->device);
+                solo = B <= 2 * (int64_t)sms;
+                if (const char *ev = getenv("KMCB200_SOLO")) solo = atoi(ev) != 0;
+            }
+            if (solo) lanes = false;
+        }
+        if (lanes || solo) {
             E.lanes_flags = (a->flags & KMCB200_FLAG_NO_MEMO) ? 1 : 0;
             for (int r = 0; r < 10; ++r) {  // Philox4x32 key schedule
                 E.rk[2 * r] = (uint32_t)a->seed + (uint32_t)r * 0x9E3779B9u;
                 E.rk[2 * r + 1] = (uint32_t)(a->seed >> 32) + (uint32_t)r * 0xBB67AE85u;
             }
+        }
+        if (lanes) {
             MemoPlan plan{0, 0};
             E.lanes_halves = 0;
             le = launch_lanes(D, E, st, nullptr, &plan);
@@ -433,7 +453,8 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
                 else lanes = false;
             }
         }
-        if (lanes) { le = launch_lanes(D, E, st, &launches); g_last_kernel = "kmc_lanes_kernel"; }
+        if (solo) { le = launch_solo(D, E, st, &launches); g_last_kernel = "kmc_solo_kernel"; }
+        else if (lanes) { le = launch_lanes(D, E, st, &launches); g_last_kernel = "kmc_lanes_kernel"; }
         else {
         g_last_kernel = narrow ? "kmc_memo_kernel" : "kmc_wide_kernel";
         // second-level entries per warp slot: enough that a trajectory's few hundred states rarely collide in the

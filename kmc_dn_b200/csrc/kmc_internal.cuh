@@ -58,6 +58,7 @@ struct EnsembleDev {
     uint32_t rk[20];
     int64_t lanes_nb_full, lanes_slice_hops;
     int lanes_ns;
+    int solo_emax;       // kmc_solo_kernel: entries of a trajectory's state graph in shared memory (set by launch_solo)
     int lanes_halves;    // 1: every block of 32 members is handed out twice and split where a run starts at member 16 (hop_lanes.cu)
     uint32_t *lanes_prog, *lanes_ck;
 };
@@ -69,6 +70,7 @@ cudaError_t launch_memo(const LayoutDev &L, const EnsembleDev &E, int logk, cuda
                         MemoPlan *plan_only = nullptr);
 cudaError_t launch_wide(const LayoutDev &L, const EnsembleDev &E, int logk, cudaStream_t st, int *launches,
                         MemoPlan *plan_only = nullptr);
+cudaError_t launch_solo(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);
 cudaError_t launch_lanes(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches,
                          MemoPlan *plan_only = nullptr);
 cudaError_t launch_reforder(const LayoutDev &L, const EnsembleDev &E, cudaStream_t st, int *launches);

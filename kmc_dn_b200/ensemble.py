@@ -11,15 +11,15 @@ import numpy as np
 
 from . import _lib
 from ._lib import (MODE_FAST, MODE_GO_SIMULATE, MODE_GO_RECORDPLUS, MODE_PY, MODE_FAST_REFORDER, MODE_PROB,  # noqa: F401
-                   FLAG_DEVICE_PTRS, FLAG_NO_MEMO, FLAG_LANES, FLAG_NO_LANES)
+                   FLAG_DEVICE_PTRS, FLAG_NO_MEMO, FLAG_LANES, FLAG_NO_LANES, FLAG_SOLO, FLAG_NO_SOLO)
 
 
 def _kernel_flags(kernel):
     """kernel: None = the library chooses; 'lanes' = thread-per-trajectory kernel (hop_lanes.cu); 'warp' = warp-per-
-    trajectory kernels (hop_memo.cu / hop_wide.cu)."""
+    trajectory kernels (hop_memo.cu / hop_wide.cu); 'solo' = latency kernel for a few trajectories (hop_lanes.cu)."""
     if kernel in (None, 'auto'):
         return 0
-    return {'lanes': FLAG_LANES, 'warp': FLAG_NO_LANES}[kernel]
+    return {'lanes': FLAG_LANES | FLAG_NO_SOLO, 'warp': FLAG_NO_LANES | FLAG_NO_SOLO, 'solo': FLAG_SOLO}[kernel]
 
 
 def _host(a, dtype):

@@ -281,7 +281,7 @@ def test_kernel_selection(golden_py):
     from kmc_dn_b200.ensemble import last_kernel
     c = golden_py["fx_rnd_min_max_0"]
     lay = _layout(c)
-    for B, want in ((70000, "kmc_lanes_kernel"), (13000, "kmc_lanes_kernel"), (100, "kmc_memo_kernel")):
+    for B, want in ((70000, "kmc_lanes_kernel"), (13000, "kmc_lanes_kernel"), (1000, "kmc_memo_kernel"), (100, "kmc_solo_kernel")):
         r = lay.run(50, c["kT"], np.tile(c["electrode_v"], (B, 1)), E_constant=np.tile(c["E_constant"], (B, 1)), seed=1)
         assert last_kernel() == want, (B, last_kernel())
         assert np.isfinite(r["time"]).all()
@@ -374,3 +374,56 @@ def test_lanes_injected_stream(golden_py):
             if to < N:
                 occ[to] = True
         assert a["time"][m] == pytest.approx(t, rel=2e-5), (m, a["time"][m], t)
+
+
+def test_solo_kernel_is_bit_identical_with_lanes_kernel(golden_py, fixtures_subset):
+    """The latency kernel (a few trajectories, one warp each, the visited states as a graph in shared memory: hop_lanes.cu,
+    kmc_solo_kernel) builds its entries with the thread-per-trajectory kernel's evaluation, draws the same variates and
+    resolves the tail with the same exact pick: time, tallies, occupation and energies are bit-identical -- on layouts
+    of 5 to 31 acceptors, 0 to 8 electrodes, with prehops, with a table of 3 or 40 entries that keeps being dropped, on a
+    dead state, for hops = 0, and for more members than CTAs."""
+    import os
+    from kmc_dn_b200.ensemble import last_kernel
+    cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
+             "c2_grid_N16_P8": golden_py["c2_grid_N16_P8"], "c1_basic_N10_P2": golden_py["c1_basic_N10_P2"],
+             "XOR_wide/test1": _fixture_case(fixtures_subset["XOR_wide/test1"]),
+             "N31_P5": synthetic_layout(31, 5, 7), "N25_P0": synthetic_layout(25, 0, 8, fill=0.5)}
+    for name, c in cases.items():
+        B, P = 6, c["P"]
+        V = np.tile(c["electrode_v"], (B, 1)) + np.arange(B)[:, None] * (1.0 if P else 0.0)
+        E = np.tile(c["E_constant"], (B, 1))
+        lay = _layout(c)
+        for hops, prehops, emax in ((4000, 0, None), (700, 300, None), (1500, 0, "3"), (1500, 100, "40"), (0, 0, None)):
+            kw = dict(E_constant=E, occupation0=c["occupation"], seed=21, prehops=prehops, want_occupation=True,
+                      want_site_energies=True)
+            ref = lay.run(hops, c["kT"], V, kernel="lanes", **kw)
+            assert last_kernel() == "kmc_lanes_kernel"
+            if emax:
+                os.environ["KMCB200_SOLO_EMAX"] = emax
+            try:
+                got = lay.run(hops, c["kT"], V, kernel="solo", **kw)
+            finally:
+                os.environ.pop("KMCB200_SOLO_EMAX", None)
+            assert last_kernel() == "kmc_solo_kernel"
+            for k in ("time", "electrode_occupation", "occupation", "site_energies"):
+                np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{name} hops={hops} prehops={prehops} emax={emax}: {k}")
+        lay.close()
+    # more members than CTAs (two per SM): the CTAs loop
+    c = golden_py["fx_rnd_min_max_0"]
+    B = 700
+    V = np.tile(c["electrode_v"], (B, 1)) + (np.arange(B) % 50)[:, None]
+    E = np.tile(c["E_constant"], (B, 1))
+    lay = _layout(c)
+    ref = lay.run(600, c["kT"], V, E_constant=E, seed=4, kernel="lanes")
+    got = lay.run(600, c["kT"], V, E_constant=E, seed=4, kernel="solo")
+    lay.close()
+    np.testing.assert_array_equal(got["time"], ref["time"])
+    np.testing.assert_array_equal(got["electrode_occupation"], ref["electrode_occupation"])
+    # a dead state
+    d = synthetic_layout(6, 0, 5)
+    d["occupation"][:] = True
+    lay = _layout(d)
+    r = lay.run(50, d["kT"], np.zeros((3, 0)), E_constant=np.tile(d["E_constant"], (3, 1)), occupation0=d["occupation"],
+                want_occupation=True, kernel="solo")
+    lay.close()
+    assert np.isinf(r["time"]).all() and r["occupation"].all()
