@@ -1027,22 +1027,26 @@ __global__ void __launch_bounds__(32) kmc_solo_kernel(const LayoutDev L, const _
             while (q < q1 && !dead) {
                 // ---- the walk (lane 0): until the block is used up or a uniform lies beyond the entry's first 6 events
                 if (lane == 0) {
-                    uint32_t a = cur;
+                    // ONE branch per hop, at the end: with an exit branch in the middle ptxas sinks two of the loads below it
+                    // and the walk pays the shared-memory latency twice per hop.  A hop that leaves has stored its entry like
+                    // the others (harmless) and moved on to a successor that is not used: the entry is read back from the store.
+                    uint32_t a = cur, pX = a_X + q * 4u;
+                    const uint32_t pEnd = a_X + q1 * 4u;
                     bool out;
-                    // (ONE branch per hop, at the end: with an exit branch in the middle ptxas sinks two of the loads below it
-                    // and the walk pays the shared-memory latency twice per hop.  The store of an exiting hop is harmless.)
                     do {
-                        const uint32_t X = lds_u(a_X + q * 4u);
+                        const uint32_t X = lds_u(pX);
                         const uint4 A = lds_u4(a), B = lds_u4(a + 16u), C = lds_u4(a + 32u);  // e0-e3 | e4 e5 s0 s1 | s2-s5
+                        sts_u(pX + 512u, a);  // (a_tr = a_X + 512)
                         out = X > B.y;
-                        sts_u(a_tr + q * 4u, a);
                         const uint32_t s01 = X > A.x ? B.w : B.z, s23 = X > A.z ? C.y : C.x, s45 = X > B.x ? C.w : C.z;
-                        const uint32_t nx = X > A.w ? s45 : (X > A.y ? s23 : s01);
-                        if (!out) {
-                            a = nx;
-                            ++q;
-                        }
-                    } while (!out && q < q1);
+                        a = X > A.w ? s45 : (X > A.y ? s23 : s01);
+                        pX += 4u;
+                    } while (!out && pX < pEnd);
+                    if (out) {
+                        pX -= 4u;
+                        a = lds_u(pX + 512u);
+                    }
+                    q = (int)((pX - a_X) >> 2);
                     cur = a;
                 }
                 q = __shfl_sync(FULL, q, 0);
@@ -1120,8 +1124,20 @@ __global__ void __launch_bounds__(32) kmc_solo_kernel(const LayoutDev L, const _
                     if (lane == e) tally += d;
                 }
             }
-            if (lane == 0)
-                for (int h = q0; h < q; ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
+            if (lane == 0) {
+                // (four hops per pair of 128-bit loads, the sums strictly in hop order)
+                int h = q0;
+                for (; h < q && (h & 3); ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
+#pragma unroll 4
+                for (; h + 4 <= q; h += 4) {
+                    const uint4 g = lds_u4(a_lg + h * 4u), r = lds_u4(a_rt + h * 4u);
+                    t_part = fmaf(__uint_as_float(g.x), __uint_as_float(r.x), t_part);
+                    t_part = fmaf(__uint_as_float(g.y), __uint_as_float(r.y), t_part);
+                    t_part = fmaf(__uint_as_float(g.z), __uint_as_float(r.z), t_part);
+                    t_part = fmaf(__uint_as_float(g.w), __uint_as_float(r.w), t_part);
+                }
+                for (; h < q; ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
+            }
             h0 = hend;
         }
 
