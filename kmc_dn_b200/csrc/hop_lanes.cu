@@ -830,28 +830,42 @@ __global__ void __launch_bounds__(32 * LANES_WARPS, LANES_MIN_CTAS) kmc_lanes_ke
 template <int PT>
 struct SoloGeom {
     using G = LanesGeom<PT>;
-    static constexpr int RINGB = 64 * 4 * 6;  // per hop of a 64-hop block: x | 0xfff, lg2(u), entry address, -ln2/total, event code, x
-    static constexpr int FIXED = G::WARP_BYTES + RINGB + (int)SOLO_HS * 2;
+    // per hop of a 64-hop block: x | 0xfff, lg2(u), entry address, -ln2/total, event code, x -- two blocks (the one being walked,
+    // the one being post-processed / refilled); then 4 control words
+    static constexpr int RINGB = 64 * 4 * 6;
+    static constexpr int FIXED = G::WARP_BYTES + 2 * RINGB + 16 + (int)SOLO_HS * 2;
 };
 
+__device__ __forceinline__ void solo_rendezvous() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+
+// Two warps per trajectory.  Warp 0 walks block b (and does everything that needs the layout: evaluations, tail picks, linking);
+// warp 1 meanwhile turns the addresses block b-1 left behind into event codes, tallies and dwell times and draws the variates of
+// block b+1.  They meet once per block (named barrier); the only other coupling: before warp 0 drops a full table it waits until
+// warp 1 has read the entries block b-1 points to (`done`).
 template <int PT, int NR>
-__global__ void __launch_bounds__(32) kmc_solo_kernel(const LayoutDev L, const __grid_constant__ EnsembleDev E) {
+__global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const __grid_constant__ EnsembleDev E) {
     using G = LanesGeom<PT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int N = L.N, S = L.S;
     const int P = PT > 0 ? PT : L.P;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int role = __shfl_sync(FULL, tid >> 5, 0);  // 0: walks, 1: helps
     {
         float2 *acc = reinterpret_cast<float2 *>(smem_raw);
         float *elF = reinterpret_cast<float *>(smem_raw + (size_t)N * ROWB);
         float *elR = elF + P * 33;
-        for (int i0 = 0; i0 < N * 33; i0 += 32)
-            if (i0 + lane < N * 33) acc[i0 + lane] = L.tblf[i0 + lane];
-        for (int i0 = 0; i0 < P * 33; i0 += 32)
-            if (i0 + lane < P * 33) {
-                const float2 v = L.tblf[N * 33 + i0 + lane];
-                elF[i0 + lane] = v.x;
-                elR[i0 + lane] = v.y;
+        for (int i0 = 0; i0 < N * 33; i0 += 64)
+            if (i0 + tid < N * 33) acc[i0 + tid] = L.tblf[i0 + tid];
+        for (int i0 = 0; i0 < P * 33; i0 += 64)
+            if (i0 + tid < P * 33) {
+                const float2 v = L.tblf[N * 33 + i0 + tid];
+                elF[i0 + tid] = v.x;
+                elR[i0 + tid] = v.y;
             }
     }
     __syncwarp();
@@ -859,302 +873,352 @@ __global__ void __launch_bounds__(32) kmc_solo_kernel(const LayoutDev L, const _
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u);
     const uint32_t a_mir = wb, a_run = wb + G::MIRB;
-    const uint32_t a_X = wb + G::WARP_BYTES, a_lg = a_X + 256u, a_tr = a_X + 512u, a_rt = a_X + 768u, a_cd = a_X + 1024u, a_xr = a_X + 1280u;
-    const uint32_t a_hash = a_X + SoloGeom<PT>::RINGB;
+    const uint32_t a_ring = wb + G::WARP_BYTES;  // block b: a_ring + (b & 1) * RINGB + {0 X, 256 lg, 512 entry, 768 rt, 1024 code, 1280 x}
+    const uint32_t a_ctl = a_ring + 2u * SoloGeom<PT>::RINGB;  // +0 `done`: blocks whose entries warp 1 has read, +4 / +8 hops done in the block (by parity), +12 dead
+    const uint32_t a_hash = a_ctl + 16u;
     const uint32_t a_ent = (a_hash + SOLO_HS * 2u + 127u) & ~127u;  // entry e at a_ent + e * 128; entry 0 is the trap
     const int emax = E.solo_emax;
-    LaneCtx ctx;
-    ctx.a_row_me = sb + lane * 8u;
-    ctx.a_col_me = sb + lane * ROWB;
-    ctx.a_elF = a_elF;
-    ctx.a_elR = a_elR;
-    ctx.a_elF_e = a_elF + lane * ELB;
-    ctx.a_elR_e = a_elR + lane * ELB;
-    ctx.a_mir = a_mir;
-    ctx.a_run = a_run;
-    ctx.accm = (1u << N) - 1u;
-    ctx.lane = lane;
-    ctx.N = N;
-    ctx.P = P;
-    ctx.lead_mask = 1u;
-    ctx.hshift = 0;
-    ctx.wtab = nullptr;
-    ctx.base = 0;
-    ctx.use_table = false;
     const int total_hops = (int)(E.prehops + E.hops), prehops = (int)E.prehops;
     // the trap: thresholds 0, so that every x leaves the walk
-    if (lane < 32) sts_u(a_ent + lane * 4u, 0u);
-    __syncwarp();
+    if (role == 0) sts_u(a_ent + lane * 4u, 0u);
+    __syncthreads();
 
     for (int64_t m = blockIdx.x; m < E.B; m += gridDim.x) {
-        // ---- member parameters (as the kernel above narrows them)
-        double E64 = 0.0;
-        if (lane < N) {
-            double e64;
-            if (E.E_constant) e64 = E.E_constant[m * N + lane];
-            else {
-                e64 = E.basis[(int64_t)P * N + lane];
-                for (int p = 0; p < P; ++p) e64 += E.electrode_v[m * P + p] * E.basis[(int64_t)p * N + lane];
-            }
-            E64 = (double)(float)e64;
-        }
-        const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;
-        const float kTt = (float)E.kT[m];
-        uint32_t occ0 = 0;
-        if (E.occupation0 && lane == 0)
-            for (int i = 0; i < N; ++i) occ0 |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
-        occ0 = __shfl_sync(FULL, occ0, 0);
         const uint64_t gm = E.member_index0 + (uint64_t)m;
         const uint32_t gm_lo = (uint32_t)gm, gm_hi = (uint32_t)(gm >> 32);
+        if (tid < 4) sts_u(a_ctl + tid * 4u, 0u);
+        __syncthreads();
 
-        int count = 0, generation = 0;  // entries in the table, times it was dropped (warp-uniform)
-        int tally = 0;                   // lane e < P: net holes into electrode e
-        double t_acc = 0.0;              // (lane 0's copy is the one that counts)
-        float t_part = 0.0f;
-        int q_mat = 0;                   // hops of the current block below q_mat have their code / rt slots filled
-
-        // event word of (entry a, X) among the 6 events of the first sector (the caller knows that X <= e5)
-        auto word_of = [&](uint32_t a, uint32_t X) {
-            const uint4 A = lds_u4(a);
-            const uint2 B = lds_u2(a + 16u);
-            return select6(X, A.x, A.y, A.z, A.w, B.x, B.y);
-        };
-        // fills code / rt of the hops [q_mat, qe) the walk went through (their slot in a_tr holds the entry they left from)
-        auto materialise = [&](int qe) {
-            __syncwarp();
-            for (int h = q_mat + lane; h < qe; h += 32) {
-                const uint32_t a = lds_u(a_tr + h * 4u);
-                if (a) {
-                    sts_u(a_cd + h * 4u, word_of(a, lds_u(a_X + h * 4u)) & 4095u);
-                    sts_u(a_rt + h * 4u, lds_u(a + 52u));
-                    sts_u(a_tr + h * 4u, 0u);
-                }
-            }
-            q_mat = qe;
-            __syncwarp();
-        };
-        auto reset = [&]() {
-            __syncwarp();
-            for (uint32_t s = lane; s < SOLO_HS / 2u; s += 32) sts_u(a_hash + s * 4u, 0u);
-            count = 0;
-            ++generation;
-            __syncwarp();
-        };
-        // entry number of state occu, 0 if it is not in the table (lane 0 probes; warp-uniform result)
-        auto lookup = [&](uint32_t occu) {
-            uint32_t found = 0;
-            if (lane == 0) {
-                uint32_t slot = (occu * 0x9E3779B1u) >> 20;  // 12 bits
-                for (;;) {
-                    const uint32_t w = lds_u(a_hash + (slot >> 1) * 4u);
-                    const uint32_t e = (slot & 1u) ? (w >> 16) : (w & 0xffffu);
-                    if (!e) break;
-                    if (lds_u(a_ent + e * SOLO_ENT + 48u) == occu) { found = e; break; }
-                    slot = (slot + 1u) & (SOLO_HS - 1u);
-                }
-            }
-            return __shfl_sync(FULL, found, 0);
-        };
-        // evaluates state occu and appends its entry (a state without any transition gets an entry without events: the walk
-        // leaves it at once, and the re-evaluation in the tail finds it dead); returns the entry number.  qd: hops of the
-        // current block done so far (their entries must be read before a full table is dropped)
-        auto insert = [&](uint32_t occu, int qd) {
-            if (count >= emax) {
-                materialise(qd);
-                reset();
-            }
-            Eval<NR> ev;
-            const bool ok = evaluate_state<PT, NR>(ctx, occu, E64, ve_mine, kTt, ev);
-            const uint32_t e = (uint32_t)++count;
-            const uint32_t a = a_ent + e * SOLO_ENT;
-            const uint32_t w = ok ? ev.word : 0u;
-            __syncwarp();
-            if (lane < 4) sts_u(a + lane * 4u, w);
-            else if (lane < 6) sts_u(a + 16u + (lane - 4) * 4u, w);
-            else if (lane < LANES_K) sts_u(a + 64u + (lane - 6) * 4u, w);
-            else if (lane == LANES_K) sts_u(a + 48u, occu);
-            else if (lane == LANES_K + 1) sts_u(a + 52u, ok ? __float_as_uint(ev.rtp) : 0u);
-            else if (lane < LANES_K + 2 + 6) sts_u(a + 24u + (lane - LANES_K - 2) * 4u, a_ent);  // successors: the trap
-            else if (lane < LANES_K + 2 + 6 + 4) sts_u(a + 96u + (lane - LANES_K - 8) * 4u, 0u);  // successors of events 6..13: unknown
-            if (lane == 0) {
-                uint32_t slot = (occu * 0x9E3779B1u) >> 20;
-                for (;;) {
-                    const uint32_t hw = lds_u(a_hash + (slot >> 1) * 4u);
-                    const uint32_t c = (slot & 1u) ? (hw >> 16) : (hw & 0xffffu);
-                    if (!c) {
-                        sts_u(a_hash + (slot >> 1) * 4u, (slot & 1u) ? (hw | (e << 16)) : (hw | e));
-                        break;
-                    }
-                    slot = (slot + 1u) & (SOLO_HS - 1u);
-                }
-            }
-            __syncwarp();
-            return e;
-        };
-
-        reset();
-        uint32_t cur = a_ent + insert(occ0, 0) * SOLO_ENT;  // address of the current state's entry (warp-uniform between walks)
-        bool dead = false;
-
-        for (int h0 = 0; h0 < total_hops && !dead;) {
-            if (h0 == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
-                t_acc = 0.0;
-                t_part = 0.0f;
-                tally = 0;
-            } else {
-                t_acc += (double)t_part;
-                t_part = 0.0f;
-            }
-            int hend = (h0 | 63) + 1;
-            if (hend > total_hops) hend = total_hops;
-            if (h0 < prehops && hend > prehops) hend = prehops;
-            const int q0 = h0 & 63, q1 = q0 + (hend - h0);
-            // ---- variates of this 64-hop block: lane l draws hops 2l and 2l+1
-            {
+        if (role == 1) {
+            // =========================================== warp 1: variates before, codes / tallies / time after ===========
+            auto gen = [&](int h0, int par) {  // lane l draws hops 2l and 2l+1 of the 64-hop block h0 lies in
+                const uint32_t rb = a_ring + (uint32_t)par * SoloGeom<PT>::RINGB;
                 const uint32_t blk0 = (uint32_t)(h0 >> 6) * 32u;
                 const uint4 r4 = philox_rk(make_uint4(blk0 + (uint32_t)lane, 0u, gm_lo, gm_hi), E.rk);
-                __syncwarp();
-                sts_f(a_lg + (2 * lane) * 4u, lg2_approx(fmaf((float)r4.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f)));
-                sts_f(a_lg + (2 * lane + 1) * 4u, lg2_approx(fmaf((float)r4.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f)));
-                sts_u(a_X + (2 * lane) * 4u, r4.y | 0xfffu);
-                sts_u(a_X + (2 * lane + 1) * 4u, r4.w | 0xfffu);
-                sts_u(a_xr + (2 * lane) * 4u, r4.y);
-                sts_u(a_xr + (2 * lane + 1) * 4u, r4.w);
-                __syncwarp();
-            }
-            int q = q0;
-            q_mat = q0;
-            while (q < q1 && !dead) {
-                // ---- the walk (lane 0): until the block is used up or a uniform lies beyond the entry's first 6 events
-                if (lane == 0) {
-                    // ONE branch per hop, at the end: with an exit branch in the middle ptxas sinks two of the loads below it
-                    // and the walk pays the shared-memory latency twice per hop.  A hop that leaves has stored its entry like
-                    // the others (harmless) and moved on to a successor that is not used: the entry is read back from the store.
-                    uint32_t a = cur, pX = a_X + q * 4u;
-                    const uint32_t pEnd = a_X + q1 * 4u;
-                    bool out;
-                    do {
-                        const uint32_t X = lds_u(pX);
-                        const uint4 A = lds_u4(a), B = lds_u4(a + 16u), C = lds_u4(a + 32u);  // e0-e3 | e4 e5 s0 s1 | s2-s5
-                        sts_u(pX + 512u, a);  // (a_tr = a_X + 512)
-                        out = X > B.y;
-                        const uint32_t s01 = X > A.x ? B.w : B.z, s23 = X > A.z ? C.y : C.x, s45 = X > B.x ? C.w : C.z;
-                        a = X > A.w ? s45 : (X > A.y ? s23 : s01);
-                        pX += 4u;
-                    } while (!out && pX < pEnd);
-                    if (out) {
-                        pX -= 4u;
-                        a = lds_u(pX + 512u);
-                    }
-                    q = (int)((pX - a_X) >> 2);
-                    cur = a;
+                sts_f(rb + 256u + (2 * lane) * 4u, lg2_approx(fmaf((float)r4.x, 2.3283064365386963e-10f, 1.1641532182693481e-10f)));
+                sts_f(rb + 256u + (2 * lane + 1) * 4u, lg2_approx(fmaf((float)r4.z, 2.3283064365386963e-10f, 1.1641532182693481e-10f)));
+                sts_u(rb + (2 * lane) * 4u, r4.y | 0xfffu);
+                sts_u(rb + (2 * lane + 1) * 4u, r4.w | 0xfffu);
+                sts_u(rb + 1280u + (2 * lane) * 4u, r4.y);
+                sts_u(rb + 1280u + (2 * lane + 1) * 4u, r4.w);
+            };
+            int tally = 0;        // lane e < P: net holes into electrode e
+            double t_acc = 0.0;   // (lane 0's copy is the one that counts)
+            float t_part = 0.0f;
+            auto post = [&](int b, int h0) {  // block b started at hop h0; the walk did its hops [q0, qd)
+                const uint32_t rb = a_ring + (uint32_t)(b & 1) * SoloGeom<PT>::RINGB;
+                const int q0 = h0 & 63, qd = (int)lds_u_volatile(a_ctl + 4u + (uint32_t)(b & 1) * 4u);
+                if (h0 == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
+                    t_acc = 0.0;
+                    t_part = 0.0f;
+                    tally = 0;
+                } else {
+                    t_acc += (double)t_part;
+                    t_part = 0.0f;
                 }
-                q = __shfl_sync(FULL, q, 0);
-                cur = __shfl_sync(FULL, cur, 0);
-                if (cur == a_ent) {
-                    // ---- the trap: hop q-1 left entry `from` by an event whose successor was not known
-                    const int qp = q - 1;
-                    const uint32_t from = lds_u(a_tr + qp * 4u);
-                    const uint32_t Xp = lds_u(a_X + qp * 4u);
-                    const uint4 A = lds_u4(from);
-                    const uint2 B = lds_u2(from + 16u);
-                    const uint32_t k = (Xp > A.x) + (Xp > A.y) + (Xp > A.z) + (Xp > A.w) + (Xp > B.x);
-                    const uint32_t code = select6(Xp, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u;
-                    const uint32_t succ = lds_u(from + 48u) ^ (bit_wrap(code) | bit_clamp((code >> 5) & 127u));
-                    uint32_t e = lookup(succ);
-                    const int gen0 = generation;
-                    if (!e) e = insert(succ, q);
-                    cur = a_ent + e * SOLO_ENT;
-                    if (generation == gen0 && lane == 0) sts_u(from + 24u + k * 4u, cur);  // (a dropped table took `from` with it)
-                    __syncwarp();
-                    continue;
-                }
-                if (q >= q1) break;
-                // ---- hop q of entry `cur` lies beyond its first 6 events: second sector, or the tail
-                const uint32_t X = lds_u(a_X + q * 4u);
-                const uint32_t occ = lds_u(cur + 48u);
-                const uint4 W2 = lds_u4(cur + 64u), W3 = lds_u4(cur + 80u);
-                uint32_t code, e = 0, k = 0;
-                float rtv = __uint_as_float(lds_u(cur + 52u));
-                const bool second = !(X > W3.w);
-                if (second) {
-                    k = (X > W2.x) + (X > W2.y) + (X > W2.z) + (X > W2.w) + (X > W3.x) + (X > W3.y) + (X > W3.z);  // event 6 + k
-                    const Sector sB = {{W2.x, W2.y, W2.z, W2.w, W3.x, W3.y, W3.z, W3.w}};
-                    code = select8(X, sB) & 4095u;
-                    const uint32_t tw = lds_u(cur + 96u + (k >> 1) * 4u);
-                    e = (k & 1u) ? (tw >> 16) : (tw & 0xffffu);
-                } else {  // tail: evaluate again, exact pick
-                    Eval<NR> ev;
-                    if (!evaluate_state<PT, NR>(ctx, occ, E64, ve_mine, kTt, ev)) {
-                        dead = true;
-                        break;
-                    }
-                    code = tail_pick<NR>(ctx, ev, occ, kTt, ve_mine, lds_u(a_xr + q * 4u));
-                    rtv = ev.rtp;
-                }
-                // this hop's code and rate go straight into its slots
-                if (lane == 0) {
-                    sts_u(a_cd + q * 4u, code);
-                    sts_f(a_rt + q * 4u, rtv);
-                    sts_u(a_tr + q * 4u, 0u);
-                }
-                const uint32_t succ = occ ^ (bit_wrap(code) | bit_clamp((code >> 5) & 127u));
-                const int gen0 = generation;
-                const uint32_t from = cur;
-                if (!e) {
-                    e = lookup(succ);
-                    if (!e) e = insert(succ, q + 1);
-                    if (second && generation == gen0 && lane == 0) {
-                        const uint32_t ap = from + 96u + (k >> 1) * 4u;
-                        const uint32_t tw = lds_u(ap);
-                        sts_u(ap, (k & 1u) ? ((tw & 0xffffu) | (e << 16)) : ((tw & 0xffff0000u) | e));
+                for (int h = q0 + lane; h < qd; h += 32) {
+                    const uint32_t a = lds_u(rb + 512u + h * 4u);
+                    if (a) {
+                        const uint32_t X = lds_u(rb + h * 4u);
+                        const uint4 A = lds_u4(a);
+                        const uint2 B = lds_u2(a + 16u);
+                        sts_u(rb + 1024u + h * 4u, select6(X, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u);
+                        sts_u(rb + 768u + h * 4u, lds_u(a + 52u));
                     }
                 }
                 __syncwarp();
-                cur = a_ent + e * SOLO_ENT;
-                ++q;
-            }
-            // ---- the block's hops [q0, q): codes and rates, then tallies (all lanes) and dwell times (lane 0, in hop order)
-            materialise(q);
-            for (int hb = q0; hb < q; hb += 32) {
-                const int h = hb + lane;
-                const uint32_t evt = (h < q) ? (lds_u(a_cd + h * 4u) >> 5) : 0u;
-                for (int e = 0; e < P; ++e) {
-                    const int d = __popc(__ballot_sync(FULL, evt == 32u + (uint32_t)e)) - __popc(__ballot_sync(FULL, evt == 64u + (uint32_t)e));
-                    if (lane == e) tally += d;
+                if (lane == 0) {  // the entries block b points to are not needed any more
+                    __threadfence_block();
+                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_ctl), "r"((uint32_t)(b + 1)) : "memory");
                 }
-            }
-            if (lane == 0) {
-                // (four hops per pair of 128-bit loads, the sums strictly in hop order)
-                int h = q0;
-                for (; h < q && (h & 3); ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
+                for (int hb = q0; hb < qd; hb += 32) {
+                    const int h = hb + lane;
+                    const uint32_t evt = (h < qd) ? (lds_u(rb + 1024u + h * 4u) >> 5) : 0u;
+                    for (int e = 0; e < P; ++e) {
+                        const int d = __popc(__ballot_sync(FULL, evt == 32u + (uint32_t)e)) - __popc(__ballot_sync(FULL, evt == 64u + (uint32_t)e));
+                        if (lane == e) tally += d;
+                    }
+                }
+                if (lane == 0) {  // four hops per pair of 128-bit loads, the sums strictly in hop order
+                    const uint32_t a_lg = rb + 256u, a_rt = rb + 768u;
+                    int h = q0;
+                    for (; h < qd && (h & 3); ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
 #pragma unroll 4
-                for (; h + 4 <= q; h += 4) {
-                    const uint4 g = lds_u4(a_lg + h * 4u), r = lds_u4(a_rt + h * 4u);
-                    t_part = fmaf(__uint_as_float(g.x), __uint_as_float(r.x), t_part);
-                    t_part = fmaf(__uint_as_float(g.y), __uint_as_float(r.y), t_part);
-                    t_part = fmaf(__uint_as_float(g.z), __uint_as_float(r.z), t_part);
-                    t_part = fmaf(__uint_as_float(g.w), __uint_as_float(r.w), t_part);
+                    for (; h + 4 <= qd; h += 4) {
+                        const uint4 g = lds_u4(a_lg + h * 4u), r = lds_u4(a_rt + h * 4u);
+                        t_part = fmaf(__uint_as_float(g.x), __uint_as_float(r.x), t_part);
+                        t_part = fmaf(__uint_as_float(g.y), __uint_as_float(r.y), t_part);
+                        t_part = fmaf(__uint_as_float(g.z), __uint_as_float(r.z), t_part);
+                        t_part = fmaf(__uint_as_float(g.w), __uint_as_float(r.w), t_part);
+                    }
+                    for (; h < qd; ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
                 }
-                for (; h < q; ++h) t_part = fmaf(lds_f(a_lg + h * 4u), lds_f(a_rt + h * 4u), t_part);
+                __syncwarp();
+            };
+            auto end_of = [&](int h0) {
+                int hend = (h0 | 63) + 1;
+                if (hend > total_hops) hend = total_hops;
+                if (h0 < prehops && hend > prehops) hend = prehops;
+                return hend;
+            };
+            if (total_hops > 0) gen(0, 0);
+            solo_rendezvous();  // the variates of block 0 are there
+            int b = 0, h_prev = 0;
+            for (int h0 = 0; h0 < total_hops; ++b) {
+                const int hend = end_of(h0);
+                if (b >= 1) post(b - 1, h_prev);
+                if (hend < total_hops) gen(hend, (b + 1) & 1);
+                h_prev = h0;
+                h0 = hend;
+                solo_rendezvous();  // block b is walked; block b-1 is accounted for; the variates of block b+1 are there
             }
-            h0 = hend;
-        }
+            if (b >= 1) post(b - 1, h_prev);
+            solo_rendezvous();
+            t_acc += (double)t_part;
+            if (lds_u_volatile(a_ctl + 12u)) t_acc = __longlong_as_double(0x7ff0000000000000LL);  // dead: +inf, as e/0 would give
+            if (lane == 0) E.time[m] = t_acc;
+            if (lane < P) E.electrode_occ[m * P + lane] = (int64_t)tally;
+        } else {
+            // =========================================== warp 0: the walk and everything that needs the layout ===========
+            LaneCtx ctx;
+            ctx.a_row_me = sb + lane * 8u;
+            ctx.a_col_me = sb + lane * ROWB;
+            ctx.a_elF = a_elF;
+            ctx.a_elR = a_elR;
+            ctx.a_elF_e = a_elF + lane * ELB;
+            ctx.a_elR_e = a_elR + lane * ELB;
+            ctx.a_mir = a_mir;
+            ctx.a_run = a_run;
+            ctx.accm = (1u << N) - 1u;
+            ctx.lane = lane;
+            ctx.N = N;
+            ctx.P = P;
+            ctx.lead_mask = 1u;
+            ctx.hshift = 0;
+            ctx.wtab = nullptr;
+            ctx.base = 0;
+            ctx.use_table = false;
+            // ---- member parameters (as the kernel above narrows them)
+            double E64 = 0.0;
+            if (lane < N) {
+                double e64;
+                if (E.E_constant) e64 = E.E_constant[m * N + lane];
+                else {
+                    e64 = E.basis[(int64_t)P * N + lane];
+                    for (int p = 0; p < P; ++p) e64 += E.electrode_v[m * P + p] * E.basis[(int64_t)p * N + lane];
+                }
+                E64 = (double)(float)e64;
+            }
+            const float ve_mine = (lane < P) ? (float)E.electrode_v[m * P + lane] : 0.0f;
+            const float kTt = (float)E.kT[m];
+            uint32_t occ0 = 0;
+            if (E.occupation0 && lane == 0)
+                for (int i = 0; i < N; ++i) occ0 |= (uint32_t)(E.occupation0[m * N + i] != 0) << i;
+            occ0 = __shfl_sync(FULL, occ0, 0);
 
-        // ---- results (time: lane 0's accumulators)
-        t_acc += (double)t_part;
-        if (dead) t_acc = __longlong_as_double(0x7ff0000000000000LL);
-        __syncwarp();
-        const uint32_t occ = lds_u(cur + 48u);
-        if (lane == 0) E.time[m] = t_acc;
-        if (lane < P) E.electrode_occ[m * P + lane] = (int64_t)tally;
-        if (E.occupation_out && lane < N) E.occupation_out[m * N + lane] = (occ >> lane) & 1u;
-        if (E.site_energies_out) {
-            if (lane < P) sts_f(a_mir + 128 + lane * 4, ve_mine);
-            if (lane < N) E.site_energies_out[m * S + lane] = energy_of(occ, ctx.accm, E64, ctx.a_row_me);
-            if (lane < P) E.site_energies_out[m * S + N + lane] = (double)ve_mine;
+            int count = 0, generation = 0;  // entries in the table, times it was dropped (warp-uniform)
+            int q_mat = 0;                   // hops of the current block below q_mat have their code / rt slots filled
+            int blk = 0;                     // block being walked
+            uint32_t rb = a_ring;            // its slots
+            // fills code / rt of the hops [q_mat, qe) the walk went through (their entry slot holds the entry they left from)
+            auto materialise = [&](int qe) {
+                __syncwarp();
+                for (int h = q_mat + lane; h < qe; h += 32) {
+                    const uint32_t a = lds_u(rb + 512u + h * 4u);
+                    if (a) {
+                        const uint32_t X = lds_u(rb + h * 4u);
+                        const uint4 A = lds_u4(a);
+                        const uint2 B = lds_u2(a + 16u);
+                        sts_u(rb + 1024u + h * 4u, select6(X, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u);
+                        sts_u(rb + 768u + h * 4u, lds_u(a + 52u));
+                        sts_u(rb + 512u + h * 4u, 0u);
+                    }
+                }
+                q_mat = qe;
+                __syncwarp();
+            };
+            auto reset = [&]() {
+                __syncwarp();
+                for (uint32_t s = lane; s < SOLO_HS / 2u; s += 32) sts_u(a_hash + s * 4u, 0u);
+                count = 0;
+                ++generation;
+                __syncwarp();
+            };
+            // entry number of state occu, 0 if it is not in the table (lane 0 probes; warp-uniform result)
+            auto lookup = [&](uint32_t occu) {
+                uint32_t found = 0;
+                if (lane == 0) {
+                    uint32_t slot = (occu * 0x9E3779B1u) >> 20;  // 12 bits
+                    for (;;) {
+                        const uint32_t w = lds_u(a_hash + (slot >> 1) * 4u);
+                        const uint32_t e = (slot & 1u) ? (w >> 16) : (w & 0xffffu);
+                        if (!e) break;
+                        if (lds_u(a_ent + e * SOLO_ENT + 48u) == occu) { found = e; break; }
+                        slot = (slot + 1u) & (SOLO_HS - 1u);
+                    }
+                }
+                return __shfl_sync(FULL, found, 0);
+            };
+            // evaluates state occu and appends its entry (a state without any transition gets an entry without events: the walk
+            // leaves it at once, and the re-evaluation in the tail finds it dead); returns the entry number.  qd: hops of the
+            // current block done so far (what they point to must be read before a full table is dropped -- and warp 1 must
+            // have read what the previous block points to)
+            auto insert = [&](uint32_t occu, int qd) {
+                if (count >= emax) {
+                    materialise(qd);
+                    while ((int)lds_u_volatile(a_ctl) < blk) {}
+                    reset();
+                }
+                Eval<NR> ev;
+                const bool ok = evaluate_state<PT, NR>(ctx, occu, E64, ve_mine, kTt, ev);
+                const uint32_t e = (uint32_t)++count;
+                const uint32_t a = a_ent + e * SOLO_ENT;
+                const uint32_t w = ok ? ev.word : 0u;
+                __syncwarp();
+                if (lane < 4) sts_u(a + lane * 4u, w);
+                else if (lane < 6) sts_u(a + 16u + (lane - 4) * 4u, w);
+                else if (lane < LANES_K) sts_u(a + 64u + (lane - 6) * 4u, w);
+                else if (lane == LANES_K) sts_u(a + 48u, occu);
+                else if (lane == LANES_K + 1) sts_u(a + 52u, ok ? __float_as_uint(ev.rtp) : 0u);
+                else if (lane < LANES_K + 2 + 6) sts_u(a + 24u + (lane - LANES_K - 2) * 4u, a_ent);  // successors: the trap
+                else if (lane < LANES_K + 2 + 6 + 4) sts_u(a + 96u + (lane - LANES_K - 8) * 4u, 0u);  // successors of events 6..13: unknown
+                if (lane == 0) {
+                    uint32_t slot = (occu * 0x9E3779B1u) >> 20;
+                    for (;;) {
+                        const uint32_t hw = lds_u(a_hash + (slot >> 1) * 4u);
+                        const uint32_t c = (slot & 1u) ? (hw >> 16) : (hw & 0xffffu);
+                        if (!c) {
+                            sts_u(a_hash + (slot >> 1) * 4u, (slot & 1u) ? (hw | (e << 16)) : (hw | e));
+                            break;
+                        }
+                        slot = (slot + 1u) & (SOLO_HS - 1u);
+                    }
+                }
+                __syncwarp();
+                return e;
+            };
+
+            reset();
+            uint32_t cur = a_ent + insert(occ0, 0) * SOLO_ENT;  // address of the current state's entry (warp-uniform between walks)
+            bool dead = false;
+            solo_rendezvous();  // the variates of block 0 are there
+
+            for (int h0 = 0; h0 < total_hops; ++blk) {
+                int hend = (h0 | 63) + 1;
+                if (hend > total_hops) hend = total_hops;
+                if (h0 < prehops && hend > prehops) hend = prehops;
+                const int q0 = h0 & 63, q1 = q0 + (hend - h0);
+                rb = a_ring + (uint32_t)(blk & 1) * SoloGeom<PT>::RINGB;
+                const uint32_t a_X = rb, a_tr = rb + 512u, a_rt = rb + 768u, a_cd = rb + 1024u, a_xr = rb + 1280u;
+                int q = q0;
+                q_mat = q0;
+                while (q < q1 && !dead) {
+                    // ---- the walk (lane 0): until the block is used up or a uniform lies beyond the entry's first 6 events
+                    if (lane == 0) {
+                        // ONE branch per hop, at the end: with an exit branch in the middle ptxas sinks two of the loads below
+                        // it and the walk pays the shared-memory latency twice per hop.  A hop that leaves has stored its entry
+                        // like the others (harmless) and moved on to a successor that is not used: the entry is read back.
+                        uint32_t a = cur, pX = a_X + q * 4u;
+                        const uint32_t pEnd = a_X + q1 * 4u;
+                        bool out;
+                        do {
+                            const uint32_t X = lds_u(pX);
+                            const uint4 A = lds_u4(a), B = lds_u4(a + 16u), C = lds_u4(a + 32u);  // e0-e3 | e4 e5 s0 s1 | s2-s5
+                            sts_u(pX + 512u, a);
+                            out = X > B.y;
+                            const uint32_t s01 = X > A.x ? B.w : B.z, s23 = X > A.z ? C.y : C.x, s45 = X > B.x ? C.w : C.z;
+                            a = X > A.w ? s45 : (X > A.y ? s23 : s01);
+                            pX += 4u;
+                        } while (!out && pX < pEnd);
+                        if (out) {
+                            pX -= 4u;
+                            a = lds_u(pX + 512u);
+                        }
+                        q = (int)((pX - a_X) >> 2);
+                        cur = a;
+                    }
+                    q = __shfl_sync(FULL, q, 0);
+                    cur = __shfl_sync(FULL, cur, 0);
+                    if (cur == a_ent) {
+                        // ---- the trap: hop q-1 left entry `from` by an event whose successor was not known
+                        const int qp = q - 1;
+                        const uint32_t from = lds_u(a_tr + qp * 4u);
+                        const uint32_t Xp = lds_u(a_X + qp * 4u);
+                        const uint4 A = lds_u4(from);
+                        const uint2 B = lds_u2(from + 16u);
+                        const uint32_t k = (Xp > A.x) + (Xp > A.y) + (Xp > A.z) + (Xp > A.w) + (Xp > B.x);
+                        const uint32_t code = select6(Xp, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u;
+                        const uint32_t succ = lds_u(from + 48u) ^ (bit_wrap(code) | bit_clamp((code >> 5) & 127u));
+                        uint32_t e = lookup(succ);
+                        const int gen0 = generation;
+                        if (!e) e = insert(succ, q);
+                        cur = a_ent + e * SOLO_ENT;
+                        if (generation == gen0 && lane == 0) sts_u(from + 24u + k * 4u, cur);  // (a dropped table took `from` with it)
+                        __syncwarp();
+                        continue;
+                    }
+                    if (q >= q1) break;
+                    // ---- hop q of entry `cur` lies beyond its first 6 events: second sector, or the tail
+                    const uint32_t X = lds_u(a_X + q * 4u);
+                    const uint32_t occ = lds_u(cur + 48u);
+                    const uint4 W2 = lds_u4(cur + 64u), W3 = lds_u4(cur + 80u);
+                    uint32_t code, e = 0, k = 0;
+                    float rtv = __uint_as_float(lds_u(cur + 52u));
+                    const bool second = !(X > W3.w);
+                    if (second) {
+                        k = (X > W2.x) + (X > W2.y) + (X > W2.z) + (X > W2.w) + (X > W3.x) + (X > W3.y) + (X > W3.z);  // event 6 + k
+                        const Sector sB = {{W2.x, W2.y, W2.z, W2.w, W3.x, W3.y, W3.z, W3.w}};
+                        code = select8(X, sB) & 4095u;
+                        const uint32_t tw = lds_u(cur + 96u + (k >> 1) * 4u);
+                        e = (k & 1u) ? (tw >> 16) : (tw & 0xffffu);
+                    } else {  // tail: evaluate again, exact pick
+                        Eval<NR> ev;
+                        if (!evaluate_state<PT, NR>(ctx, occ, E64, ve_mine, kTt, ev)) {
+                            dead = true;
+                            break;
+                        }
+                        code = tail_pick<NR>(ctx, ev, occ, kTt, ve_mine, lds_u(a_xr + q * 4u));
+                        rtv = ev.rtp;
+                    }
+                    // this hop's code and rate go straight into its slots
+                    if (lane == 0) {
+                        sts_u(a_cd + q * 4u, code);
+                        sts_f(a_rt + q * 4u, rtv);
+                        sts_u(a_tr + q * 4u, 0u);
+                    }
+                    const uint32_t succ = occ ^ (bit_wrap(code) | bit_clamp((code >> 5) & 127u));
+                    const int gen0 = generation;
+                    const uint32_t from = cur;
+                    if (!e) {
+                        e = lookup(succ);
+                        if (!e) e = insert(succ, q + 1);
+                        if (second && generation == gen0 && lane == 0) {
+                            const uint32_t ap = from + 96u + (k >> 1) * 4u;
+                            const uint32_t tw = lds_u(ap);
+                            sts_u(ap, (k & 1u) ? ((tw & 0xffffu) | (e << 16)) : ((tw & 0xffff0000u) | e));
+                        }
+                    }
+                    __syncwarp();
+                    cur = a_ent + e * SOLO_ENT;
+                    ++q;
+                }
+                if (lane == 0) {
+                    sts_u(a_ctl + 4u + (uint32_t)(blk & 1) * 4u, (uint32_t)q);  // hops [q0, q) of this block are done
+                    if (dead) sts_u(a_ctl + 12u, 1u);
+                }
+                h0 = hend;
+                solo_rendezvous();  // (warp 1: block blk-1 accounted for, variates of block blk+1 drawn)
+            }
+            solo_rendezvous();  // warp 1 has accounted for the last block
+            const uint32_t occ = lds_u(cur + 48u);
+            if (E.occupation_out && lane < N) E.occupation_out[m * N + lane] = (occ >> lane) & 1u;
+            if (E.site_energies_out) {
+                if (lane < P) sts_f(a_mir + 128 + lane * 4, ve_mine);
+                if (lane < N) E.site_energies_out[m * S + lane] = energy_of(occ, ctx.accm, E64, ctx.a_row_me);
+                if (lane < P) E.site_energies_out[m * S + N + lane] = (double)ve_mine;
+            }
         }
-        __syncwarp();
+        __syncthreads();
     }
 }
 
@@ -1180,7 +1244,7 @@ static cudaError_t launch_solo_t(const LayoutDev &L, EnsembleDev E, cudaStream_t
     if (err != cudaSuccess) return err;
     const int64_t cap = (int64_t)sms * per_sm;
     const unsigned grid = (unsigned)(E.B < cap ? E.B : cap);
-    kern<<<grid, 32, smem, st>>>(L, E);
+    kern<<<grid, 64, smem, st>>>(L, E);
     if (launches) ++*launches;
     return cudaGetLastError();
 }
