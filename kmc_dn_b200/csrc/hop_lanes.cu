@@ -830,13 +830,27 @@ __global__ void __launch_bounds__(32 * LANES_WARPS, LANES_MIN_CTAS) kmc_lanes_ke
 template <int PT>
 struct SoloGeom {
     using G = LanesGeom<PT>;
-    // per hop of a 64-hop block: x | 0xfff, lg2(u), entry address, -ln2/total, event code, x -- two blocks (the one being walked,
-    // the one being post-processed / refilled); then 4 control words
+    // per hop of a 64-hop block: x | 0xfff, lg2(u), entry address, -ln2/total, event code, x -- three blocks (the one being walked,
+    // the one being accounted for, the one being filled with variates); then 8 control words
     static constexpr int RINGB = 64 * 4 * 6;
-    static constexpr int FIXED = G::WARP_BYTES + 2 * RINGB + 16 + (int)SOLO_HS * 2;
+    static constexpr int FIXED = G::WARP_BYTES + 3 * RINGB + 32 + (int)SOLO_HS * 2;
 };
 
-__device__ __forceinline__ void solo_rendezvous() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+// (not inlined: both warps meet at the SAME instruction, which is what compute-sanitizer's synccheck expects of a barrier that
+// counts every thread of the CTA)
+__device__ __noinline__ void solo_rendezvous() {
+    __syncwarp();  // (bar.sync is the .aligned form: the warp must arrive as one)
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+}
+// warp 1 has read the entries the previous block points to (does not wait) / warp 0 waits for that
+__device__ __forceinline__ void solo_entries_read() {
+    __syncwarp();
+    asm volatile("bar.arrive 2, 64;" ::: "memory");
+}
+__device__ __forceinline__ void solo_wait_entries_read() {
+    __syncwarp();
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t lds_u_volatile(uint32_t a) {
     uint32_t v;
     asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
@@ -845,8 +859,9 @@ __device__ __forceinline__ uint32_t lds_u_volatile(uint32_t a) {
 
 // Two warps per trajectory.  Warp 0 walks block b (and does everything that needs the layout: evaluations, tail picks, linking);
 // warp 1 meanwhile turns the addresses block b-1 left behind into event codes, tallies and dwell times and draws the variates of
-// block b+1.  They meet once per block (named barrier); the only other coupling: before warp 0 drops a full table it waits until
-// warp 1 has read the entries block b-1 points to (`done`).
+// block b+1.  They meet once per block (named barrier 1).  Before that warp 1 signals (arrives at barrier 2, without waiting) that
+// it has read the entries block b-1 points to; warp 0 waits for that signal at the end of its walk, when it came long ago -- or
+// earlier, if it has to drop a full table.
 template <int PT, int NR>
 __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const __grid_constant__ EnsembleDev E) {
     using G = LanesGeom<PT>;
@@ -873,9 +888,9 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
     const uint32_t a_elF = sb + (uint32_t)N * ROWB, a_elR = a_elF + (uint32_t)P * ELB;
     const uint32_t wb = sb + (((uint32_t)N * ROWB + 2u * (uint32_t)P * ELB + 15u) & ~15u);
     const uint32_t a_mir = wb, a_run = wb + G::MIRB;
-    const uint32_t a_ring = wb + G::WARP_BYTES;  // block b: a_ring + (b & 1) * RINGB + {0 X, 256 lg, 512 entry, 768 rt, 1024 code, 1280 x}
-    const uint32_t a_ctl = a_ring + 2u * SoloGeom<PT>::RINGB;  // +0 `done`: blocks whose entries warp 1 has read, +4 / +8 hops done in the block (by parity), +12 dead
-    const uint32_t a_hash = a_ctl + 16u;
+    const uint32_t a_ring = wb + G::WARP_BYTES;  // block b: a_ring + (b % 3) * RINGB + {0 X, 256 lg, 512 entry, 768 rt, 1024 code, 1280 x}
+    const uint32_t a_ctl = a_ring + 3u * SoloGeom<PT>::RINGB;  // +0 / +4 / +8: hops done in the block (by b % 3), +12 dead
+    const uint32_t a_hash = a_ctl + 32u;
     const uint32_t a_ent = (a_hash + SOLO_HS * 2u + 127u) & ~127u;  // entry e at a_ent + e * 128; entry 0 is the trap
     const int emax = E.solo_emax;
     const int total_hops = (int)(E.prehops + E.hops), prehops = (int)E.prehops;
@@ -886,7 +901,7 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
     for (int64_t m = blockIdx.x; m < E.B; m += gridDim.x) {
         const uint64_t gm = E.member_index0 + (uint64_t)m;
         const uint32_t gm_lo = (uint32_t)gm, gm_hi = (uint32_t)(gm >> 32);
-        if (tid < 4) sts_u(a_ctl + tid * 4u, 0u);
+        if (tid < 8) sts_u(a_ctl + tid * 4u, 0u);
         __syncthreads();
 
         if (role == 1) {
@@ -905,9 +920,9 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
             int tally = 0;        // lane e < P: net holes into electrode e
             double t_acc = 0.0;   // (lane 0's copy is the one that counts)
             float t_part = 0.0f;
-            auto post = [&](int b, int h0) {  // block b started at hop h0; the walk did its hops [q0, qd)
-                const uint32_t rb = a_ring + (uint32_t)(b & 1) * SoloGeom<PT>::RINGB;
-                const int q0 = h0 & 63, qd = (int)lds_u_volatile(a_ctl + 4u + (uint32_t)(b & 1) * 4u);
+            auto post = [&](int ri, int h0) {  // the block in ring slot ri started at hop h0; the walk did its hops [q0, qd)
+                const uint32_t rb = a_ring + (uint32_t)ri * SoloGeom<PT>::RINGB;
+                const int q0 = h0 & 63, qd = (int)lds_u(a_ctl + (uint32_t)ri * 4u);
                 if (h0 == prehops && prehops > 0) {  // kmc_dopant_networks.py:580-585: tallies restart, occupation is kept
                     t_acc = 0.0;
                     t_part = 0.0f;
@@ -926,11 +941,7 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                         sts_u(rb + 768u + h * 4u, lds_u(a + 52u));
                     }
                 }
-                __syncwarp();
-                if (lane == 0) {  // the entries block b points to are not needed any more
-                    __threadfence_block();
-                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(a_ctl), "r"((uint32_t)(b + 1)) : "memory");
-                }
+                solo_entries_read();  // the entries that block points to are not needed any more: warp 0 may drop the table
                 for (int hb = q0; hb < qd; hb += 32) {
                     const int h = hb + lane;
                     const uint32_t evt = (h < qd) ? (lds_u(rb + 1024u + h * 4u) >> 5) : 0u;
@@ -963,19 +974,20 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
             };
             if (total_hops > 0) gen(0, 0);
             solo_rendezvous();  // the variates of block 0 are there
-            int b = 0, h_prev = 0;
+            int b = 0, h_prev = 0, ri = 0;  // ri = b % 3
             for (int h0 = 0; h0 < total_hops; ++b) {
                 const int hend = end_of(h0);
-                if (b >= 1) post(b - 1, h_prev);
-                if (hend < total_hops) gen(hend, (b + 1) & 1);
+                if (hend < total_hops) gen(hend, ri == 2 ? 0 : ri + 1);
+                if (b >= 1) post(ri == 0 ? 2 : ri - 1, h_prev);  // (meets warp 0 once inside)
                 h_prev = h0;
                 h0 = hend;
+                ri = ri == 2 ? 0 : ri + 1;
                 solo_rendezvous();  // block b is walked; block b-1 is accounted for; the variates of block b+1 are there
             }
-            if (b >= 1) post(b - 1, h_prev);
+            if (b >= 1) post(ri == 0 ? 2 : ri - 1, h_prev);
             solo_rendezvous();
             t_acc += (double)t_part;
-            if (lds_u_volatile(a_ctl + 12u)) t_acc = __longlong_as_double(0x7ff0000000000000LL);  // dead: +inf, as e/0 would give
+            if (lds_u(a_ctl + 12u)) t_acc = __longlong_as_double(0x7ff0000000000000LL);  // dead: +inf, as e/0 would give
             if (lane == 0) E.time[m] = t_acc;
             if (lane < P) E.electrode_occ[m * P + lane] = (int64_t)tally;
         } else {
@@ -1018,7 +1030,8 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
 
             int count = 0, generation = 0;  // entries in the table, times it was dropped (warp-uniform)
             int q_mat = 0;                   // hops of the current block below q_mat have their code / rt slots filled
-            int blk = 0;                     // block being walked
+            int ri = 0;                      // ring slot of the block being walked (block number % 3)
+            bool met = false;                // this block's first meeting with warp 1 is behind us
             uint32_t rb = a_ring;            // its slots
             // fills code / rt of the hops [q_mat, qe) the walk went through (their entry slot holds the entry they left from)
             auto materialise = [&](int qe) {
@@ -1066,7 +1079,10 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
             auto insert = [&](uint32_t occu, int qd) {
                 if (count >= emax) {
                     materialise(qd);
-                    while ((int)lds_u_volatile(a_ctl) < blk) {}
+                    if (!met) {
+                        solo_wait_entries_read();
+                        met = true;
+                    }
                     reset();
                 }
                 Eval<NR> ev;
@@ -1103,12 +1119,13 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
             bool dead = false;
             solo_rendezvous();  // the variates of block 0 are there
 
-            for (int h0 = 0; h0 < total_hops; ++blk) {
+            met = true;  // (nothing of an earlier block is left before block 0)
+            for (int h0 = 0; h0 < total_hops; ri = ri == 2 ? 0 : ri + 1) {
                 int hend = (h0 | 63) + 1;
                 if (hend > total_hops) hend = total_hops;
                 if (h0 < prehops && hend > prehops) hend = prehops;
                 const int q0 = h0 & 63, q1 = q0 + (hend - h0);
-                rb = a_ring + (uint32_t)(blk & 1) * SoloGeom<PT>::RINGB;
+                rb = a_ring + (uint32_t)ri * SoloGeom<PT>::RINGB;
                 const uint32_t a_X = rb, a_tr = rb + 512u, a_rt = rb + 768u, a_cd = rb + 1024u, a_xr = rb + 1280u;
                 int q = q0;
                 q_mat = q0;
@@ -1203,12 +1220,15 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                     ++q;
                 }
                 if (lane == 0) {
-                    sts_u(a_ctl + 4u + (uint32_t)(blk & 1) * 4u, (uint32_t)q);  // hops [q0, q) of this block are done
+                    sts_u(a_ctl + (uint32_t)ri * 4u, (uint32_t)q);  // hops [q0, q) of this block are done
                     if (dead) sts_u(a_ctl + 12u, 1u);
                 }
                 h0 = hend;
-                solo_rendezvous();  // (warp 1: block blk-1 accounted for, variates of block blk+1 drawn)
+                if (!met) solo_wait_entries_read();  // (warp 1 has read what the previous block points to: normally long ago)
+                solo_rendezvous();            // (warp 1: the previous block accounted for, variates of the next block drawn)
+                met = false;
             }
+            if (!met) solo_wait_entries_read();
             solo_rendezvous();  // warp 1 has accounted for the last block
             const uint32_t occ = lds_u(cur + 48u);
             if (E.occupation_out && lane < N) E.occupation_out[m * N + lane] = (occ >> lane) & 1u;
