@@ -220,11 +220,13 @@ def test_bench_refuses_to_run_without_gpu():
 
 
 def test_kernel_choice_argument():
-    """`kernel=` of Layout.run maps onto the C ABI's KMCB200_FLAG_LANES / _NO_LANES; unknown names are refused."""
+    """`kernel=` of Layout.run maps onto the C ABI's KMCB200_FLAG_LANES / _NO_LANES / _SOLO / _NO_SOLO; unknown names are refused."""
     from kmc_dn_b200 import _lib
     from kmc_dn_b200.ensemble import _kernel_flags
     assert _kernel_flags(None) == 0 and _kernel_flags("auto") == 0
-    assert _kernel_flags("lanes") == _lib.FLAG_LANES == 4 and _kernel_flags("warp") == _lib.FLAG_NO_LANES == 8
+    assert _lib.FLAG_LANES == 4 and _lib.FLAG_NO_LANES == 8 and _lib.FLAG_SOLO == 16 and _lib.FLAG_NO_SOLO == 32  # include/kmc_b200.h
+    assert _kernel_flags("lanes") == _lib.FLAG_LANES | _lib.FLAG_NO_SOLO and _kernel_flags("warp") == _lib.FLAG_NO_LANES | _lib.FLAG_NO_SOLO
+    assert _kernel_flags("solo") == _lib.FLAG_SOLO
     with pytest.raises(KeyError):
         _kernel_flags("fastest")
     header = open(os.path.join(ROOT, "include", "kmc_b200.h")).read()
