@@ -126,6 +126,10 @@ __device__ __forceinline__ uint32_t select6(uint32_t X, uint32_t a, uint32_t b, 
     const uint32_t s01 = X > a ? b : a, s23 = X > c ? d : c, s45 = X > e ? f : e;
     return X > d ? s45 : (X > b ? s23 : s01);
 }
+__device__ __forceinline__ uint32_t select4(uint32_t X, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t s01 = X > a ? b : a, s23 = X > c ? d : c;
+    return X > b ? s23 : s01;
+}
 __device__ __forceinline__ uint32_t select8(uint32_t X, const Sector &s) {
     const uint32_t s01 = X > s.w[0] ? s.w[1] : s.w[0], s23 = X > s.w[2] ? s.w[3] : s.w[2];
     const uint32_t s45 = X > s.w[4] ? s.w[5] : s.w[4], s67 = X > s.w[6] ? s.w[7] : s.w[6];
@@ -814,17 +818,17 @@ __global__ void __launch_bounds__(32 * LANES_WARPS, LANES_MIN_CTAS) kmc_lanes_ke
 // mask update, tallies and the next hash: 90 ns per hop on the warp-per-trajectory kernel against 28 ns on one CPU core with
 // the reference's cache.  Here one warp owns one trajectory and keeps the states it has visited as a GRAPH in shared memory:
 // an entry holds the event words of the kernel above (same evaluate_state, same tail_pick: results are bit-identical with
-// kmc_lanes_kernel) and, for each of its 6 most likely events, the shared-memory ADDRESS of the successor's entry.  Lane 0
-// WALKS the graph and does nothing else: per hop three 128-bit shared loads at a known address, six compares, five selects on
+// kmc_lanes_kernel) and, for each of its 4 most likely events, the shared-memory ADDRESS of the successor's entry.  Lane 0
+// WALKS the graph and does nothing else: per hop two 128-bit shared loads at a known address, four compares, three selects on
 // the successor addresses, one store of the address it was at.  No hash, no mask, no tallies, no time on the chain.  A
 // successor that is not known yet points to a trap entry whose thresholds send the walk to the exit it already has for the
-// rare events (beyond the 6 most likely ones).  Everything else is done by all 32 lanes for 64 hops at a time: the variates
+// rare events (beyond the 4 most likely ones: 0.2-0.8 % of the hops on C3).  Everything else is done by all 32 lanes for 64 hops at a time: the variates
 // before the walk (Philox numbering of the kernels above), and after it -- from the addresses the walk left behind -- event codes,
 // electrode tallies (ballots) and the dwell times (one lane, in hop order: fp32 sums must not be re-associated).  Leaving
 // the walk: the warp resolves the event (second sector, or evaluate + tail_pick), finds or evaluates the successor (lane =
 // acceptor, as above) and links it.  A table that fills up is dropped and rebuilt (a pure cache).  Record outputs, traces and
 // injected streams stay on the kernels above.
-#define SOLO_ENT 128u    // bytes per entry: e0-e3 | e4 e5 s0 s1 | s2-s5 | key rt - - | e6-e9 | e10-e13 | t6..t13 (u16) | -
+#define SOLO_ENT 128u    // bytes per entry: e0-e3 | s0-s3 | key rt e4 e5 | e6-e9 | e10-e13 | t4..t13 (u16 entry numbers) | -
 #define SOLO_HS 4096u    // slots of the mask -> entry hash (u16 entry numbers, 0 = empty)
 
 template <int PT>
@@ -936,9 +940,8 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                     if (a) {
                         const uint32_t X = lds_u(rb + h * 4u);
                         const uint4 A = lds_u4(a);
-                        const uint2 B = lds_u2(a + 16u);
-                        sts_u(rb + 1024u + h * 4u, select6(X, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u);
-                        sts_u(rb + 768u + h * 4u, lds_u(a + 52u));
+                        sts_u(rb + 1024u + h * 4u, select4(X, A.x, A.y, A.z, A.w) & 4095u);
+                        sts_u(rb + 768u + h * 4u, lds_u(a + 36u));
                     }
                 }
                 solo_entries_read();  // the entries that block points to are not needed any more: warp 0 may drop the table
@@ -1041,9 +1044,8 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                     if (a) {
                         const uint32_t X = lds_u(rb + h * 4u);
                         const uint4 A = lds_u4(a);
-                        const uint2 B = lds_u2(a + 16u);
-                        sts_u(rb + 1024u + h * 4u, select6(X, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u);
-                        sts_u(rb + 768u + h * 4u, lds_u(a + 52u));
+                        sts_u(rb + 1024u + h * 4u, select4(X, A.x, A.y, A.z, A.w) & 4095u);
+                        sts_u(rb + 768u + h * 4u, lds_u(a + 36u));
                         sts_u(rb + 512u + h * 4u, 0u);
                     }
                 }
@@ -1066,7 +1068,7 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                         const uint32_t w = lds_u(a_hash + (slot >> 1) * 4u);
                         const uint32_t e = (slot & 1u) ? (w >> 16) : (w & 0xffffu);
                         if (!e) break;
-                        if (lds_u(a_ent + e * SOLO_ENT + 48u) == occu) { found = e; break; }
+                        if (lds_u(a_ent + e * SOLO_ENT + 32u) == occu) { found = e; break; }
                         slot = (slot + 1u) & (SOLO_HS - 1u);
                     }
                 }
@@ -1092,12 +1094,12 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                 const uint32_t w = ok ? ev.word : 0u;
                 __syncwarp();
                 if (lane < 4) sts_u(a + lane * 4u, w);
-                else if (lane < 6) sts_u(a + 16u + (lane - 4) * 4u, w);
-                else if (lane < LANES_K) sts_u(a + 64u + (lane - 6) * 4u, w);
-                else if (lane == LANES_K) sts_u(a + 48u, occu);
-                else if (lane == LANES_K + 1) sts_u(a + 52u, ok ? __float_as_uint(ev.rtp) : 0u);
-                else if (lane < LANES_K + 2 + 6) sts_u(a + 24u + (lane - LANES_K - 2) * 4u, a_ent);  // successors: the trap
-                else if (lane < LANES_K + 2 + 6 + 4) sts_u(a + 96u + (lane - LANES_K - 8) * 4u, 0u);  // successors of events 6..13: unknown
+                else if (lane < 6) sts_u(a + 40u + (lane - 4) * 4u, w);
+                else if (lane < LANES_K) sts_u(a + 48u + (lane - 6) * 4u, w);
+                else if (lane == LANES_K) sts_u(a + 32u, occu);
+                else if (lane == LANES_K + 1) sts_u(a + 36u, ok ? __float_as_uint(ev.rtp) : 0u);
+                else if (lane < LANES_K + 2 + 4) sts_u(a + 16u + (lane - LANES_K - 2) * 4u, a_ent);  // successors of events 0..3: the trap
+                else if (lane < LANES_K + 2 + 4 + 5) sts_u(a + 80u + (lane - LANES_K - 6) * 4u, 0u);  // successors of events 4..13: unknown
                 if (lane == 0) {
                     uint32_t slot = (occu * 0x9E3779B1u) >> 20;
                     for (;;) {
@@ -1130,7 +1132,7 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                 int q = q0;
                 q_mat = q0;
                 while (q < q1 && !dead) {
-                    // ---- the walk (lane 0): until the block is used up or a uniform lies beyond the entry's first 6 events
+                    // ---- the walk (lane 0): until the block is used up or a uniform lies beyond the entry's first 4 events
                     if (lane == 0) {
                         // ONE branch per hop, at the end: with an exit branch in the middle ptxas sinks two of the loads below
                         // it and the walk pays the shared-memory latency twice per hop.  A hop that leaves has stored its entry
@@ -1140,11 +1142,11 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                         bool out;
                         do {
                             const uint32_t X = lds_u(pX);
-                            const uint4 A = lds_u4(a), B = lds_u4(a + 16u), C = lds_u4(a + 32u);  // e0-e3 | e4 e5 s0 s1 | s2-s5
+                            const uint4 A = lds_u4(a), Sx = lds_u4(a + 16u);  // e0-e3 | s0-s3
                             sts_u(pX + 512u, a);
-                            out = X > B.y;
-                            const uint32_t s01 = X > A.x ? B.w : B.z, s23 = X > A.z ? C.y : C.x, s45 = X > B.x ? C.w : C.z;
-                            a = X > A.w ? s45 : (X > A.y ? s23 : s01);
+                            out = X > A.w;
+                            const uint32_t s01 = X > A.x ? Sx.y : Sx.x, s23 = X > A.z ? Sx.w : Sx.z;
+                            a = X > A.y ? s23 : s01;
                             pX += 4u;
                         } while (!out && pX < pEnd);
                         if (out) {
@@ -1162,31 +1164,36 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                         const uint32_t from = lds_u(a_tr + qp * 4u);
                         const uint32_t Xp = lds_u(a_X + qp * 4u);
                         const uint4 A = lds_u4(from);
-                        const uint2 B = lds_u2(from + 16u);
-                        const uint32_t k = (Xp > A.x) + (Xp > A.y) + (Xp > A.z) + (Xp > A.w) + (Xp > B.x);
-                        const uint32_t code = select6(Xp, A.x, A.y, A.z, A.w, B.x, B.y) & 4095u;
-                        const uint32_t succ = lds_u(from + 48u) ^ (bit_wrap(code) | bit_clamp((code >> 5) & 127u));
+                        const uint32_t k = (Xp > A.x) + (Xp > A.y) + (Xp > A.z);
+                        const uint32_t code = select4(Xp, A.x, A.y, A.z, A.w) & 4095u;
+                        const uint32_t succ = lds_u(from + 32u) ^ (bit_wrap(code) | bit_clamp((code >> 5) & 127u));
                         uint32_t e = lookup(succ);
                         const int gen0 = generation;
                         if (!e) e = insert(succ, q);
                         cur = a_ent + e * SOLO_ENT;
-                        if (generation == gen0 && lane == 0) sts_u(from + 24u + k * 4u, cur);  // (a dropped table took `from` with it)
+                        if (generation == gen0 && lane == 0) sts_u(from + 16u + k * 4u, cur);  // (a dropped table took `from` with it)
                         __syncwarp();
                         continue;
                     }
                     if (q >= q1) break;
-                    // ---- hop q of entry `cur` lies beyond its first 6 events: second sector, or the tail
+                    // ---- hop q of entry `cur` lies beyond its first 4 events: events 4 .. 13, or the tail
                     const uint32_t X = lds_u(a_X + q * 4u);
-                    const uint32_t occ = lds_u(cur + 48u);
-                    const uint4 W2 = lds_u4(cur + 64u), W3 = lds_u4(cur + 80u);
+                    const uint4 W1 = lds_u4(cur + 32u), W2 = lds_u4(cur + 48u), W3 = lds_u4(cur + 64u);  // key rt e4 e5 | e6-e9 | e10-e13
+                    const uint32_t occ = W1.x;
                     uint32_t code, e = 0, k = 0;
-                    float rtv = __uint_as_float(lds_u(cur + 52u));
+                    float rtv = __uint_as_float(W1.y);
                     const bool second = !(X > W3.w);
                     if (second) {
-                        k = (X > W2.x) + (X > W2.y) + (X > W2.z) + (X > W2.w) + (X > W3.x) + (X > W3.y) + (X > W3.z);  // event 6 + k
-                        const Sector sB = {{W2.x, W2.y, W2.z, W2.w, W3.x, W3.y, W3.z, W3.w}};
-                        code = select8(X, sB) & 4095u;
-                        const uint32_t tw = lds_u(cur + 96u + (k >> 1) * 4u);
+                        const uint32_t ws[10] = {W1.z, W1.w, W2.x, W2.y, W2.z, W2.w, W3.x, W3.y, W3.z, W3.w};
+                        uint32_t word = ws[0];
+#pragma unroll
+                        for (int j = 0; j < 9; ++j)
+                            if (X > ws[j]) {  // (the words ascend: the last j with X > ws[j] decides)
+                                k = (uint32_t)j + 1u;
+                                word = ws[j + 1];
+                            }
+                        code = word & 4095u;  // event 4 + k
+                        const uint32_t tw = lds_u(cur + 80u + (k >> 1) * 4u);
                         e = (k & 1u) ? (tw >> 16) : (tw & 0xffffu);
                     } else {  // tail: evaluate again, exact pick
                         Eval<NR> ev;
@@ -1210,7 +1217,7 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                         e = lookup(succ);
                         if (!e) e = insert(succ, q + 1);
                         if (second && generation == gen0 && lane == 0) {
-                            const uint32_t ap = from + 96u + (k >> 1) * 4u;
+                            const uint32_t ap = from + 80u + (k >> 1) * 4u;
                             const uint32_t tw = lds_u(ap);
                             sts_u(ap, (k & 1u) ? ((tw & 0xffffu) | (e << 16)) : ((tw & 0xffff0000u) | e));
                         }
@@ -1230,7 +1237,7 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
             }
             if (!met) solo_wait_entries_read();
             solo_rendezvous();  // warp 1 has accounted for the last block
-            const uint32_t occ = lds_u(cur + 48u);
+            const uint32_t occ = lds_u(cur + 32u);
             if (E.occupation_out && lane < N) E.occupation_out[m * N + lane] = (occ >> lane) & 1u;
             if (E.site_energies_out) {
                 if (lane < P) sts_f(a_mir + 128 + lane * 4, ve_mine);
