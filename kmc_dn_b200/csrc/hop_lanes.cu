@@ -1139,16 +1139,33 @@ __global__ void __launch_bounds__(64) kmc_solo_kernel(const LayoutDev L, const _
                         // like the others (harmless) and moved on to a successor that is not used: the entry is read back.
                         uint32_t a = cur, pX = a_X + q * 4u;
                         const uint32_t pEnd = a_X + q1 * 4u;
-                        bool out;
-                        do {
-                            const uint32_t X = lds_u(pX);
-                            const uint4 A = lds_u4(a), Sx = lds_u4(a + 16u);  // e0-e3 | s0-s3
-                            sts_u(pX + 512u, a);
-                            out = X > A.w;
-                            const uint32_t s01 = X > A.x ? Sx.y : Sx.x, s23 = X > A.z ? Sx.w : Sx.z;
-                            a = X > A.y ? s23 : s01;
-                            pX += 4u;
-                        } while (!out && pX < pEnd);
+                        bool out = false;
+                        // one hop: entry loads, the store of where we are, exit test, successor; the exit branch comes last
+#define SOLO_HOP(Xv)                                                                                                   \
+    {                                                                                                                  \
+        const uint32_t X = (Xv);                                                                                       \
+        const uint4 A = lds_u4(a), Sx = lds_u4(a + 16u); /* e0-e3 | s0-s3 */                                           \
+        sts_u(pX + 512u, a);                                                                                           \
+        out = X > A.w;                                                                                                 \
+        const uint32_t s01 = X > A.x ? Sx.y : Sx.x, s23 = X > A.z ? Sx.w : Sx.z;                                       \
+        a = X > A.y ? s23 : s01;                                                                                       \
+        pX += 4u;                                                                                                      \
+    }
+                        // (the variates four at a time where the block allows it: the lone warp is bound by the number of
+                        // shared-memory instructions it can issue as much as by their latency)
+                        while (!out && pX < pEnd && (pX & 15u)) SOLO_HOP(lds_u(pX));
+                        while (!out && pX + 16u <= pEnd) {
+                            const uint4 X4 = lds_u4(pX);
+                            SOLO_HOP(X4.x);
+                            if (out) break;
+                            SOLO_HOP(X4.y);
+                            if (out) break;
+                            SOLO_HOP(X4.z);
+                            if (out) break;
+                            SOLO_HOP(X4.w);
+                        }
+                        while (!out && pX < pEnd) SOLO_HOP(lds_u(pX));
+#undef SOLO_HOP
                         if (out) {
                             pX -= 4u;
                             a = lds_u(pX + 512u);
