@@ -380,8 +380,8 @@ def test_solo_kernel_is_bit_identical_with_lanes_kernel(golden_py, fixtures_subs
     """The latency kernel (a few trajectories, one warp each, the visited states as a graph in shared memory: hop_lanes.cu,
     kmc_solo_kernel) builds its entries with the thread-per-trajectory kernel's evaluation, draws the same variates and
     resolves the tail with the same exact pick: time, tallies, occupation and energies are bit-identical -- on layouts
-    of 5 to 31 acceptors, 0 to 8 electrodes, with prehops, with a table of 3 or 40 entries that keeps being dropped, on a
-    dead state, for hops = 0, and for more members than CTAs."""
+    of 5 to 31 acceptors, 0 to 8 electrodes, with prehops, with a table of 3 or 40 entries that keeps being dropped, on 24
+    random layouts / fillings / temperatures, on a dead state, for hops = 0, and for more members than CTAs."""
     import os
     from kmc_dn_b200.ensemble import last_kernel
     cases = {"fx_rnd_min_max_0": golden_py["fx_rnd_min_max_0"], "n5_p3_hot": golden_py["n5_p3_hot"],
@@ -408,6 +408,28 @@ def test_solo_kernel_is_bit_identical_with_lanes_kernel(golden_py, fixtures_subs
             for k in ("time", "electrode_occupation", "occupation", "site_energies"):
                 np.testing.assert_array_equal(got[k], ref[k], err_msg=f"{name} hops={hops} prehops={prehops} emax={emax}: {k}")
         lay.close()
+    # random layouts, fillings and temperatures
+    rng = np.random.default_rng(77)
+    for t in range(24):
+        N, P = int(rng.integers(3, 32)), int(rng.integers(0, 9))
+        c = synthetic_layout(N, P, 100 + t, fill=float(rng.uniform(0.15, 0.9)))
+        B = 3
+        V = np.tile(c["electrode_v"], (B, 1)) + rng.normal(0, 5, size=(B, P))
+        E = np.tile(c["E_constant"], (B, 1))
+        kT = c["kT"] * float(rng.choice([0.3, 1.0, 4.0]))
+        lay = _layout(c)
+        kw = dict(E_constant=E, occupation0=c["occupation"], seed=int(rng.integers(1 << 30)), prehops=int(rng.choice([0, 130])),
+                  want_occupation=True, want_site_energies=True)
+        ref = lay.run(2500, kT, V, kernel="lanes", **kw)
+        if t % 2:
+            os.environ["KMCB200_SOLO_EMAX"] = "7"
+        try:
+            got = lay.run(2500, kT, V, kernel="solo", **kw)
+        finally:
+            os.environ.pop("KMCB200_SOLO_EMAX", None)
+        lay.close()
+        for k in ("time", "electrode_occupation", "occupation", "site_energies"):
+            np.testing.assert_array_equal(got[k], ref[k], err_msg=f"random layout {t} (N={N}, P={P}): {k}")
     # more members than CTAs (two per SM): the CTAs loop
     c = golden_py["fx_rnd_min_max_0"]
     B = 700
