@@ -49,6 +49,13 @@
 // slice-major with a per-block progress flag, so that the launch does not end on a few warps finishing whole blocks
 // (round 1: SMs active 88 % of the launch).
 //
+// Halves.  An ensemble whose blocks would leave more than half of the device's warp slots empty gives every block two warps;
+// a block splits where a run of identical members starts at member 16 (see the kernel).  Geometry: CTAs of 14 warps, two per
+// SM (72 registers), which keeps shared memory at 117 KB per SM and L1 at 124 KB.
+//
+// The same file holds kmc_solo_kernel, the latency kernel for a FEW trajectories (one warp walks a trajectory's visited states
+// as a graph in shared memory, a second warp does the bookkeeping): same evaluation, same entries, bit-identical results.
+//
 // RNG: Philox4x32-10 (key = seed, counter = (64-hop block * 32 + pair, global member index), two hops per call), so
 // streams do not depend on batching, on the number of GPUs or on the kernel's geometry.  The round keys come
 // precomputed from the host (EnsembleDev::rk, constant bank operands).
