@@ -127,7 +127,7 @@ enum {
     KMCB200_FLAG_NO_LANES = 8,    /* MODE_FAST: never use the thread-per-trajectory kernel                 */
     KMCB200_FLAG_SOLO = 16,       /* MODE_FAST, N <= 31, fewer than 2^31 hops, no record / trace / injected-stream outputs:
                                      force the latency kernel (one warp per trajectory, the visited states as a graph in
-                                     shared memory; default: chosen for ensembles of at most 2 members per SM)         */
+                                     shared memory; default: chosen for ensembles of at most 8 members per SM)         */
     KMCB200_FLAG_NO_SOLO = 32     /* MODE_FAST: never use the latency kernel                                       */
 };
 

@@ -363,7 +363,7 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
         }
         // ---- latency kernel: a few trajectories (the drop-in's single go_simulation call), one warp each, the visited states
         //      as a graph in shared memory (hop_lanes.cu, kmc_solo_kernel): 3 x faster per trajectory than a warp of the
-        //      memoised kernel as long as every trajectory has a CTA of its own
+        //      memoised kernel as long as every trajectory has a CTA of its own, and ahead of it up to 8 members per SM
         bool solo = false;
         {
             const bool solo_ok = narrow && th < kLanesMaxHops && !(a->flags & KMCB200_FLAG_NO_MEMO) && !E.trace && !E.misses &&
@@ -374,7 +374,10 @@ extern "C" int kmcb200_run_ensemble(kmcb200_layout *lay, const kmcb200_ensemble_
             } else if (solo_ok && !(a->flags & (KMCB200_FLAG_NO_SOLO | KMCB200_FLAG_LANES))) {
                 int sms = 0;
                 cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, lay->device);
-                solo = B <= 2 * (int64_t)sms;
+                // (two CTAs per SM run at once; beyond that the CTAs take several members in turn -- still ahead of a warp per
+                // trajectory up to ~2000 members: C3, distinct members, 1e5 hops: 512 members 4.4e9 against 1.7e9 hops/s, 1184: 4.4e9
+                // against 3.6e9, 2048: 5.7e9 against 6.1e9; profiles/r02/exp9_solo_cutoff.py)
+                solo = B <= 8 * (int64_t)sms;
                 if (const char *ev = getenv("KMCB200_SOLO")) solo = atoi(ev) != 0;
             }
             if (solo) lanes = false;

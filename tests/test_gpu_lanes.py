@@ -281,7 +281,7 @@ def test_kernel_selection(golden_py):
     from kmc_dn_b200.ensemble import last_kernel
     c = golden_py["fx_rnd_min_max_0"]
     lay = _layout(c)
-    for B, want in ((70000, "kmc_lanes_kernel"), (13000, "kmc_lanes_kernel"), (1000, "kmc_memo_kernel"), (100, "kmc_solo_kernel")):
+    for B, want in ((70000, "kmc_lanes_kernel"), (13000, "kmc_lanes_kernel"), (3000, "kmc_memo_kernel"), (1000, "kmc_solo_kernel"), (100, "kmc_solo_kernel")):
         r = lay.run(50, c["kT"], np.tile(c["electrode_v"], (B, 1)), E_constant=np.tile(c["E_constant"], (B, 1)), seed=1)
         assert last_kernel() == want, (B, last_kernel())
         assert np.isfinite(r["time"]).all()
